@@ -1,0 +1,601 @@
+// lsb_kernels.cuh -- sm_100a device code of the LSD radix sort hot path.
+//
+// Reference path being replaced (citations relative to /root/reference/):
+//   generator loop ............ mpi/mpi_lsbsort.cpp:650-656   -> generate_kernel
+//   localShuffle count ........ mpi/mpi_lsbsort.cpp:226-229   -> hist_kernel / seg_count_kernel
+//   count transpose + scan .... mpi/mpi_lsbsort.cpp:327-479   -> scan kernels (digit-major, rank-minor)
+//   localShuffle scatter,
+//   pack / alltoallv / unpack . mpi/mpi_lsbsort.cpp:241-246,530-576 -> partition_kernel
+//   verify .................... mpi/mpi_lsbsort.cpp:710-739   -> verify_kernel / checksum
+//
+// Everything here is integer/byte work bound by HBM (and NVLink for G > 1); no tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lsb {
+
+typedef unsigned __int128 u128;
+
+struct __align__(16) Elt {
+  uint64_t key;
+  uint64_t val;
+};
+
+// ------------------------------------------------------------------------------------
+// memory helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ Elt ld_stream(const Elt* p) {
+  Elt e;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(e.key), "=l"(e.val) : "l"(p));
+  return e;
+}
+__device__ __forceinline__ uint64_t ld_stream_key(const Elt* p) {
+  uint64_t k;
+  asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(k) : "l"(p));
+  return k;
+}
+__device__ __forceinline__ void st_elt(Elt* p, const Elt& e) {
+  asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(e.key), "l"(e.val) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_gpu(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ------------------------------------------------------------------------------------
+// PCG64 (setseq_xsl_rr_128_64 with the default stream), the generator pcg64(myRank)
+// of mpi/mpi_lsbsort.cpp:650-653.  Not vendored by the reference (mpi/getpcg.sh:3);
+// restated from the published algorithm: 128-bit LCG, advance first, XSL-RR output.
+// ------------------------------------------------------------------------------------
+#define LSB_PCG_MULT_HI 2549297995355413924ULL
+#define LSB_PCG_MULT_LO 4865540595714422341ULL
+#define LSB_PCG_INC_HI 6364136223846793005ULL
+#define LSB_PCG_INC_LO 1442695040888963407ULL
+
+__host__ __device__ __forceinline__ u128 mk128(uint64_t hi, uint64_t lo) { return ((u128)hi << 64) | lo; }
+__host__ __device__ __forceinline__ u128 pcg_mult() { return mk128(LSB_PCG_MULT_HI, LSB_PCG_MULT_LO); }
+__host__ __device__ __forceinline__ u128 pcg_inc() { return mk128(LSB_PCG_INC_HI, LSB_PCG_INC_LO); }
+__host__ __device__ __forceinline__ u128 pcg_seed(uint64_t seed) {
+  return ((u128)seed + pcg_inc()) * pcg_mult() + pcg_inc();
+}
+__host__ __device__ __forceinline__ uint64_t pcg_output(u128 s) {
+  uint64_t hi = (uint64_t)(s >> 64), lo = (uint64_t)s;
+  unsigned rot = (unsigned)(hi >> 58);
+  uint64_t x = hi ^ lo;
+  return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+// affine map x -> mult*x + plus that equals `delta` LCG steps (Brown's jump-ahead)
+__host__ __device__ inline void pcg_jump_coeffs(u128 delta, u128& acc_mult, u128& acc_plus) {
+  u128 cur_mult = pcg_mult(), cur_plus = pcg_inc();
+  acc_mult = 1;
+  acc_plus = 0;
+  while (delta > 0) {
+    if (delta & 1) {
+      acc_mult *= cur_mult;
+      acc_plus = acc_plus * cur_mult + cur_plus;
+    }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+}
+
+struct GenArgs {
+  Elt* dst;             // shard base
+  int64_t first_global; // global index of dst[0]
+  int64_t count;        // elements of this shard (here)
+  int64_t per_stream;   // ceil(n / R): slots per pcg stream
+  uint64_t seed_base;
+  uint64_t key_mask;
+  int32_t and_draws;    // k
+  // affine map for a jump of 32*k draws (one warp row)
+  uint64_t row_mult_hi, row_mult_lo, row_plus_hi, row_plus_lo;
+};
+
+constexpr int GEN_ROWS = 64;       // rows of 32 elements per warp
+constexpr int GEN_THREADS = 256;
+
+// Warp w owns GEN_ROWS consecutive rows of 32 elements; lane l owns column l, so every
+// store is a coalesced 512-byte row.  A lane walks its column with the precomputed
+// 32*k-step affine map and only pays the O(log) jump-ahead when it (re)enters a stream.
+__global__ void __launch_bounds__(GEN_THREADS) generate_kernel(const GenArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * GEN_THREADS + threadIdx.x) >> 5;
+  const int64_t chunk0 = warp * (32 * GEN_ROWS);
+  if (chunk0 >= a.count) return;
+  const u128 mult = pcg_mult(), inc = pcg_inc();
+  const u128 row_mult = mk128(a.row_mult_hi, a.row_mult_lo), row_plus = mk128(a.row_plus_hi, a.row_plus_lo);
+  const int k = a.and_draws;
+  u128 state = 0;
+  int64_t stream_end = -1;  // global index where the current stream ends (exclusive)
+  for (int t = 0; t < GEN_ROWS; t++) {
+    const int64_t li = chunk0 + (int64_t)t * 32 + lane;
+    if (li >= a.count) break;
+    const int64_t gi = a.first_global + li;
+    if (gi >= stream_end) {  // first row, or crossed into the next rank's stream
+      const int64_t r = gi / a.per_stream;
+      const int64_t j = gi - r * a.per_stream;
+      u128 jm, jp;
+      pcg_jump_coeffs((u128)j * (u128)k, jm, jp);
+      state = jm * pcg_seed(a.seed_base + (uint64_t)r) + jp;
+      stream_end = (r + 1) * a.per_stream;
+    }
+    u128 s = state;
+    uint64_t key = ~0ULL;
+    for (int d = 0; d < k; d++) {
+      s = s * mult + inc;
+      key &= pcg_output(s);
+    }
+    Elt e;
+    e.key = key & a.key_mask;
+    e.val = (uint64_t)gi;
+    st_elt(a.dst + li, e);
+    state = state * row_mult + row_plus;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// count kernels (localShuffle's count loop, mpi/mpi_lsbsort.cpp:226-229)
+// ------------------------------------------------------------------------------------
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_MAX_SUB = 16;
+
+struct HistArgs {
+  const Elt* src;
+  int64_t m;
+  int32_t nsub;
+  int32_t shift[HIST_MAX_SUB];
+  uint32_t mask[HIST_MAX_SUB];
+  unsigned long long* out;  // [nsub][256], accumulated with atomics (caller zeroes)
+};
+
+// warp-aggregated shared-memory increment: when the whole warp hits one bin (the
+// skewed-key case: upper digits all zero) one lane adds the population count instead of
+// 32 serialised same-address atomics.
+__device__ __forceinline__ void smem_count(unsigned* hist, unsigned bin, unsigned active) {
+  int all_same;
+  __match_all_sync(active, bin, &all_same);
+  if (all_same) {
+    if ((threadIdx.x & 31) == (__ffs(active) - 1)) atomicAdd(hist + bin, __popc(active));
+  } else {
+    atomicAdd(hist + bin, 1u);
+  }
+}
+
+// One read of the shard produces the 256-bin histograms of up to 16 sub-digits (every
+// sub-pass of a single-GPU sort): block-private shared-memory histograms, coalesced
+// 8-byte key loads with 4 loads in flight per thread, one global atomic per bin per CTA.
+__global__ void __launch_bounds__(HIST_THREADS) hist_kernel(const HistArgs a) {
+  __shared__ unsigned sh[HIST_MAX_SUB * 256];
+  for (int i = threadIdx.x; i < a.nsub * 256; i += HIST_THREADS) sh[i] = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * HIST_THREADS;
+  int64_t i = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+  constexpr int U = 4;
+  for (; i + (U - 1) * stride < a.m; i += U * stride) {
+    uint64_t k[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) k[u] = ld_stream_key(a.src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      for (int s = 0; s < a.nsub; s++)
+        smem_count(sh + s * 256, (unsigned)(k[u] >> a.shift[s]) & a.mask[s], 0xffffffffu);
+  }
+  for (; i < a.m; i += stride) {
+    unsigned active = __activemask();
+    uint64_t k = ld_stream_key(a.src + i);
+    for (int s = 0; s < a.nsub; s++) smem_count(sh + s * 256, (unsigned)(k >> a.shift[s]) & a.mask[s], active);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < a.nsub * 256; j += HIST_THREADS)
+    if (sh[j]) atomicAdd(a.out + j, (unsigned long long)sh[j]);
+}
+
+// Per-shard counts of a full (up to 16-bit) digit over a buffer that is already grouped
+// by the digit's low `lo_bits` (segment s = low bits, seg_start[s] .. seg_start[s+1]):
+// inside a segment only the high sub-digit varies, so a 256-bin shared histogram per
+// (CTA, segment piece) suffices.  out[(hi << lo_bits) | s].
+struct SegCountArgs {
+  const Elt* src;
+  int64_t m;
+  const int64_t* seg_start;  // [nseg + 1]
+  int32_t lo_bits;
+  int32_t shift_hi;
+  uint32_t mask_hi;
+  unsigned long long* out;   // [256 << lo_bits], caller zeroes
+};
+
+__global__ void __launch_bounds__(HIST_THREADS) seg_count_kernel(const SegCountArgs a) {
+  __shared__ unsigned sh[256];
+  __shared__ int s_seg_lo;
+  const int nseg = 1 << a.lo_bits;
+  // contiguous chunk of this CTA, multiple of HIST_THREADS elements
+  int64_t chunk = (a.m + gridDim.x - 1) / gridDim.x;
+  chunk = (chunk + HIST_THREADS - 1) / HIST_THREADS * HIST_THREADS;
+  const int64_t c0 = (int64_t)blockIdx.x * chunk;
+  const int64_t c1 = (c0 + chunk < a.m) ? c0 + chunk : a.m;
+  if (c0 >= c1) return;
+  if (threadIdx.x == 0) {  // last segment whose start is <= c0
+    int lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (a.seg_start[mid] <= c0) lo = mid; else hi = mid;
+    }
+    s_seg_lo = lo;
+  }
+  if (threadIdx.x < 256) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int seg = s_seg_lo; seg < nseg; seg++) {
+    const int64_t b = a.seg_start[seg] > c0 ? a.seg_start[seg] : c0;
+    const int64_t e = a.seg_start[seg + 1] < c1 ? a.seg_start[seg + 1] : c1;
+    if (a.seg_start[seg] >= c1) break;
+    if (b >= e) continue;
+    for (int64_t i = b + threadIdx.x; i < e; i += HIST_THREADS) {
+      unsigned active = __activemask();
+      uint64_t k = ld_stream_key(a.src + i);
+      smem_count(sh, (unsigned)(k >> a.shift_hi) & a.mask_hi, active);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      unsigned c = sh[threadIdx.x];
+      if (c) atomicAdd(a.out + (((size_t)threadIdx.x << a.lo_bits) | (unsigned)seg), (unsigned long long)c);
+      sh[threadIdx.x] = 0;
+    }
+    __syncthreads();
+  }
+}
+
+// test hook (lsb_histogram): dense count of a full digit in whatever order the shard is in
+__global__ void dense_count_kernel(const Elt* src, int64_t m, int shift, uint32_t mask, unsigned long long* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+    atomicAdd(out + ((unsigned)(ld_stream_key(src + i) >> shift) & mask), 1ULL);
+}
+
+// ------------------------------------------------------------------------------------
+// scans
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// blockDim.x == 256: exclusive scan of one 256-bin histogram per block.
+// out[b*257 + 0..255] = exclusive prefix, out[b*257 + 256] = total.
+__global__ void __launch_bounds__(256) scan256_kernel(const unsigned long long* hist, int64_t* out) {
+  __shared__ uint64_t wtot[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint64_t c = hist[(size_t)blockIdx.x * 256 + t];
+  const uint64_t incl = warp_incl_scan(c);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t off = 0;
+  for (int i = 0; i < w; i++) off += wtot[i];
+  out[(size_t)blockIdx.x * 257 + t] = (int64_t)(off + incl - c);
+  if (t == 255) out[(size_t)blockIdx.x * 257 + 256] = (int64_t)(off + incl);
+}
+
+// tiles per segment -> exclusive prefix (nseg <= 256, blockDim.x == 256)
+__global__ void __launch_bounds__(256) seg_tiles_kernel(const int64_t* seg_start, int nseg, int tile,
+                                                        uint32_t* seg_tile_start) {
+  __shared__ uint64_t wtot[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  uint64_t c = 0;
+  if (t < nseg) c = (uint64_t)((seg_start[t + 1] - seg_start[t] + tile - 1) / tile);
+  const uint64_t incl = warp_incl_scan(c);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t off = 0;
+  for (int i = 0; i < w; i++) off += wtot[i];
+  if (t < nseg) seg_tile_start[t] = (uint32_t)(off + incl - c);
+  if (t == nseg - 1) seg_tile_start[nseg] = (uint32_t)(off + incl);
+}
+
+// The reference's copyCountsToGlobalCounts + exclusiveScan + copyStartsFromGlobalStarts
+// (mpi/mpi_lsbsort.cpp:327-479) in one kernel: exclusive scan of counts[g][d] in
+// digit-major, rank-minor order (dstGlobalIdx = d*R + rank, :350) and extraction of this
+// rank's column: mybase[d] = GlobalStarts[d*G + my].  Also the elements this rank sends to
+// each destination shard (sendCounts, :553-554).  One CTA of 1024 threads; the table is
+// at most 65536 x 8 counts.
+struct GlobalScanArgs {
+  const unsigned long long* counts;  // [G][nb]
+  int32_t nb;
+  int32_t G;
+  int32_t my;
+  int64_t per;                       // destination shard size
+  int64_t* mybase;                   // [nb]
+  unsigned long long* sent;          // [G] (caller zeroes) or nullptr
+};
+
+__global__ void __launch_bounds__(1024) global_scan_kernel(const GlobalScanArgs a) {
+  __shared__ uint64_t wtot[32];
+  __shared__ unsigned long long s_sent[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t < 8) s_sent[t] = 0;
+  const int chunk = (a.nb + 1023) / 1024;
+  const int d0 = t * chunk, d1 = min(d0 + chunk, a.nb);
+  uint64_t local = 0;
+  for (int d = d0; d < d1; d++)
+    for (int g = 0; g < a.G; g++) local += a.counts[(size_t)g * a.nb + d];
+  const uint64_t incl = warp_incl_scan(local);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t run = incl - local;
+  for (int i = 0; i < w; i++) run += wtot[i];
+  unsigned long long sent[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int d = d0; d < d1; d++)
+    for (int g = 0; g < a.G; g++) {
+      const uint64_t c = a.counts[(size_t)g * a.nb + d];
+      if (g == a.my) {
+        a.mybase[d] = (int64_t)run;
+        if (c && a.sent) {  // split [run, run+c) over destination shards
+          uint64_t b = run, e = run + c;
+          while (b < e) {
+            const uint64_t r = b / (uint64_t)a.per;
+            const uint64_t lim = (r + 1) * (uint64_t)a.per;
+            const uint64_t x = e < lim ? e : lim;
+            sent[r] += x - b;
+            b = x;
+          }
+        }
+      }
+      run += c;
+    }
+  if (a.sent) {
+    for (int g = 0; g < a.G; g++)
+      if (sent[g]) atomicAdd(&s_sent[g], sent[g]);
+    __syncthreads();
+    if (t < a.G) a.sent[t] = s_sent[t];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// partition kernel: one stable counting-sort step on a sub-digit of <= 8 bits.
+//
+// This is localShuffle's scatter (:241-246) and, for the last sub-digit of a pass, also
+// the pack / MPI_Alltoallv / unpack exchange (:530-576): the destination index is the
+// GLOBAL output index, and the 16-byte store goes straight into the destination GPU's
+// shard (peer pointer over NVLink) -- no 24-byte ShuffleBufSortElement, no staging.
+//
+// Shape: tiles of PT_TILE elements taken in input order (dynamic tile id), ranks inside
+// the tile from warp match_any + warp-private shared histograms, cross-tile offsets per
+// bin by decoupled look-back over 64-bit {tag, count} words, tile re-ordered through
+// shared memory so that every bin's run leaves as consecutive 16-byte vector stores.
+// The input may be split into segments (already grouped by the low sub-digit); a tile never
+// straddles a segment, look-back restarts at each segment, and bin bases are per segment.
+// ------------------------------------------------------------------------------------
+constexpr int PT_THREADS = 512;
+constexpr int PT_WARPS = PT_THREADS / 32;
+constexpr int PT_IPT = 8;
+constexpr int PT_TILE = PT_THREADS * PT_IPT;  // 4096 elements = 64 KiB
+constexpr int PT_SMEM = PT_TILE * 16 + PT_WARPS * 256 * 4 + 256 * 4 + 256 * 8;
+
+constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
+
+struct PartArgs {
+  const Elt* src;
+  int32_t shift;
+  uint32_t mask;
+  int32_t seg_bits;                // nseg = 1 << seg_bits
+  const int64_t* seg_start;        // [nseg + 1] element offsets into src
+  const uint32_t* seg_tile_start;  // [nseg + 1] tile-index prefix
+  const int64_t* bases;            // [(bin << seg_bits) | seg]: global output index of this shard's
+                                   // first element of (seg, bin)
+  uint64_t* lookback;              // [tiles][256]
+  uint32_t* tile_counter;
+  uint64_t tag_agg;                // (2*gen+1) << 56
+  uint64_t tag_inc;                // (2*gen+2) << 56
+  int64_t per;                     // destination shard size (global index / per = shard)
+  int32_t world;
+  Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
+};
+
+__global__ void __launch_bounds__(PT_THREADS, 2) partition_kernel(const PartArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Elt* s_sorted = reinterpret_cast<Elt*>(smem);
+  unsigned* s_whist = reinterpret_cast<unsigned*>(smem + PT_TILE * 16);
+  unsigned* s_binstart = s_whist + PT_WARPS * 256;
+  long long* s_bindst = reinterpret_cast<long long*>(s_binstart + 256);
+  __shared__ int s_tile, s_seg, s_count, s_first;
+  __shared__ long long s_begin;
+  __shared__ unsigned s_wtot[8];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) {
+    const unsigned tile = atomicAdd(a.tile_counter, 1u);
+    const int nseg = 1 << a.seg_bits;
+    if (tile >= a.seg_tile_start[nseg]) {
+      s_tile = -1;
+    } else {
+      int lo = 0, hi = nseg;  // last segment whose first tile is <= tile
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (a.seg_tile_start[mid] <= tile) lo = mid; else hi = mid;
+      }
+      const unsigned t_in = tile - a.seg_tile_start[lo];
+      const long long begin = a.seg_start[lo] + (long long)t_in * PT_TILE;
+      const long long end = a.seg_start[lo + 1];
+      s_tile = (int)tile;
+      s_seg = lo;
+      s_begin = begin;
+      s_count = (int)((end - begin < PT_TILE) ? (end - begin) : PT_TILE);
+      s_first = (t_in == 0);
+    }
+  }
+  for (int i = tid; i < PT_WARPS * 256; i += PT_THREADS) s_whist[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile < 0) return;
+  const int count = s_count;
+  const int seg = s_seg;
+
+  // ---- load: warp-striped, PT_IPT independent 16-byte loads in flight per thread ----
+  Elt e[PT_IPT];
+  const int idx0 = warp * (32 * PT_IPT) + lane;
+  {
+    const Elt* src = a.src + s_begin + idx0;
+#pragma unroll
+    for (int j = 0; j < PT_IPT; j++) {
+      if (idx0 + j * 32 < count) e[j] = ld_stream(src + j * 32);
+      else { e[j].key = 0; e[j].val = 0; }
+    }
+  }
+
+  // ---- rank inside the warp, in input order (stable) ----
+  unsigned* wh = s_whist + warp * 256;
+  unsigned rank[PT_IPT];
+  const unsigned lt = lanemask_lt();
+#pragma unroll
+  for (int j = 0; j < PT_IPT; j++) {
+    const bool valid = idx0 + j * 32 < count;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    rank[j] = 0;
+    if (valid) {
+      const unsigned bin = (unsigned)(e[j].key >> a.shift) & a.mask;
+      const unsigned peers = __match_any_sync(vmask, bin);
+      const unsigned old = wh[bin];
+      __syncwarp(vmask);
+      if ((peers & lt) == 0) wh[bin] = old + __popc(peers);
+      __syncwarp(vmask);
+      rank[j] = old + __popc(peers & lt);
+    }
+  }
+  __syncthreads();
+
+  // ---- per-bin: exclusive over warps, tile total, publish aggregate early ----
+  unsigned tile_count = 0;
+  uint64_t* my_state = nullptr;
+  if (tid < 256) {
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; w++) {
+      const unsigned c = s_whist[w * 256 + tid];
+      s_whist[w * 256 + tid] = tile_count;
+      tile_count += c;
+    }
+    my_state = a.lookback + (size_t)tile * 256 + tid;
+    st_relaxed_gpu(my_state, (s_first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
+    // exclusive scan of tile totals over the 256 bins
+    unsigned incl = tile_count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    s_binstart[tid] = incl - tile_count;  // exclusive inside the warp; warp offset added below
+  }
+  __syncthreads();
+  if (tid < 256) {
+    unsigned off = 0;
+    for (int i = 0; i < warp; i++) off += s_wtot[i];
+    s_binstart[tid] += off;
+  }
+  __syncthreads();
+
+  // ---- reorder the tile through shared memory ----
+#pragma unroll
+  for (int j = 0; j < PT_IPT; j++) {
+    if (idx0 + j * 32 < count) {
+      const unsigned bin = (unsigned)(e[j].key >> a.shift) & a.mask;
+      const unsigned p = s_binstart[bin] + wh[bin] + rank[j];
+      s_sorted[p] = e[j];
+    }
+  }
+
+  // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
+  if (tid < 256) {
+    uint64_t excl = 0;
+    if (!s_first) {
+      int look = tile - 1;
+      while (true) {
+        const uint64_t v = ld_relaxed_gpu(a.lookback + (size_t)look * 256 + tid);
+        const uint64_t tag = v & ~LB_VALUE_MASK;
+        if (tag == a.tag_inc) { excl += v & LB_VALUE_MASK; break; }
+        if (tag == a.tag_agg) { excl += v & LB_VALUE_MASK; look--; continue; }
+        __nanosleep(20);
+      }
+      st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
+    }
+    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)s_binstart[tid];
+  }
+  __syncthreads();
+
+  // ---- write: consecutive threads -> consecutive slots of a bin's run ----
+#pragma unroll
+  for (int k = 0; k < PT_IPT; k++) {
+    const int p = k * PT_THREADS + tid;
+    if (p < count) {
+      const Elt el = s_sorted[p];
+      const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
+      long long g = s_bindst[bin] + p;
+      Elt* out;
+      if (a.world == 1) {
+        out = a.dst[0] + g;
+      } else {
+        int r = 0;
+        for (int q = 1; q < a.world; q++) r += (g >= (long long)q * a.per);
+        out = a.dst[r] + (g - (long long)r * a.per);
+      }
+      st_elt(out, el);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// verification: strictly increasing (key,val) + multiset hash (mpi/mpi_lsbsort.cpp:710-739)
+// ------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t k, uint64_t v) {
+  uint64_t x = k * 0x9E3779B97F4A7C15ULL + (v ^ 0xD6E8FEB86659FD93ULL);
+  x ^= x >> 32; x *= 0xD6E8FEB86659FD93ULL;
+  x ^= x >> 29; x *= 0x9E3779B97F4A7C15ULL;
+  x ^= x >> 32;
+  return x;
+}
+
+// out[0..3] = checksum (sum mix, xor mix, xor key, sum val); out[4] = order violations
+__global__ void __launch_bounds__(256) verify_kernel(const Elt* src, int64_t m, unsigned long long* out) {
+  uint64_t s = 0, x = 0, xk = 0, sv = 0, bad = 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+    const Elt e = ld_stream(src + i);
+    const uint64_t h = mix64(e.key, e.val);
+    s += h; x ^= h; xk ^= e.key; sv += e.val;
+    if (i > 0) {
+      const Elt p = ld_stream(src + i - 1);
+      if (p.key > e.key || (p.key == e.key && p.val >= e.val)) bad++;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, d);
+    x ^= __shfl_xor_sync(0xffffffffu, x, d);
+    xk ^= __shfl_xor_sync(0xffffffffu, xk, d);
+    sv += __shfl_xor_sync(0xffffffffu, sv, d);
+    bad += __shfl_xor_sync(0xffffffffu, bad, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 0, (unsigned long long)s);
+    atomicXor(out + 1, (unsigned long long)x);
+    atomicXor(out + 2, (unsigned long long)xk);
+    atomicAdd(out + 3, (unsigned long long)sv);
+    if (bad) atomicAdd(out + 4, (unsigned long long)bad);
+  }
+}
+
+}  // namespace lsb

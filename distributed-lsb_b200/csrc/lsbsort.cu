@@ -1,0 +1,783 @@
+// lsbsort.cu -- C ABI (include/lsbsort.h) over the sm_100a kernels in lsb_kernels.cuh.
+//
+// Host-side restatement of the reference's pass structure, mpi/mpi_lsbsort.cpp:481-585
+// (globalShuffle / mySort), for device-resident shards.  A reference pass on a digit of
+// up to 16 bits is executed as one or two stable 8-bit counting-sort steps:
+//
+//   G == 1 : [low sub-digit] A -> B, [high sub-digit] B -> A, both over the whole shard,
+//            with every 256-bin histogram of the whole sort taken in ONE up-front read.
+//   G  > 1 : [low sub-digit] local A -> B (shard becomes grouped by the low bits =
+//            "segments"), count of the full digit per segment, NCCL all-gather of the
+//            counts + digit-major/rank-minor exclusive scan (== :327-479), then
+//            [high sub-digit] B -> A where the destination is the GLOBAL output index and
+//            the store goes directly into the owning GPU's shard over NVLink (== :530-576).
+//
+// Two stable steps (low bits, then high bits) are exactly one stable step on the full
+// digit, so the array after each pass is bit-identical to the reference's.
+#include "../../include/lsbsort.h"
+#include "lsb_kernels.cuh"
+
+#include <nccl.h>  // types only: the library itself is bound at run time, see NcclApi
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lsb;
+
+namespace {
+
+struct SubPass {
+  int shift;
+  int bits;
+};
+
+struct PassPlan {
+  int shift;    // first bit of the digit
+  int bits;     // width of the digit (radix_bits, or the remainder for the last pass)
+  int lo_bits;  // low sub-digit width (0 if the digit fits one step)
+  int hi_bits;
+};
+
+}  // namespace
+
+struct lsb_ctx {
+  lsb_config cfg;
+  int G = 1, my = 0;
+  int64_t n = 0, per = 0, here = 0, first = 0, per_stream = 0;
+  int npasses = 0;
+  cudaStream_t stream = nullptr;
+  Elt* buf[2] = {nullptr, nullptr};  // A, B
+  int cur = 0;                        // which of buf[] holds the data
+  Elt* peer[2][LSB_MAX_GPUS] = {};    // peer[b][g]: shard b of GPU g (own pointer for g == my)
+  bool peer_open[2][LSB_MAX_GPUS] = {};
+  uint64_t* lookback = nullptr;
+  size_t lookback_tiles = 0;
+  uint32_t* tile_counters = nullptr;  // [64]
+  int next_counter = 0;
+  int gen = 0;
+  unsigned long long* hist = nullptr;        // [HIST_MAX_SUB][256]
+  int64_t* scan_out = nullptr;               // [HIST_MAX_SUB][257]
+  unsigned long long* counts_local = nullptr;  // [65536]
+  unsigned long long* counts_all = nullptr;    // [G][65536]
+  int64_t* mybase = nullptr;                 // [65536]
+  uint32_t* seg_tile_start = nullptr;        // [257]
+  int64_t* one_seg_start = nullptr;          // {0, here}
+  uint32_t* one_seg_tiles = nullptr;         // {0, ceil(here/TILE)}
+  unsigned long long* small = nullptr;       // [64] scratch: sent[8], verify[5], barrier word, gather
+  unsigned long long* small_all = nullptr;   // [G][16]
+  unsigned long long* host_small = nullptr;  // pinned [8*16 + 64]
+  ncclComm_t comm = nullptr;
+  bool comm_ready = false;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  std::vector<cudaEvent_t> phase_ev;
+  std::vector<int> phase_kind;  // 0 hist, 1 scan/collective, 2 partition
+  int64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+thread_local std::string g_create_err;
+
+// NCCL is bound with dlopen on first multi-GPU use instead of at link time: a process that
+// also hosts PyTorch must end up with ONE libnccl.so.2 (torch's bundled 2.28 needs symbols the
+// system 2.27 lacks), so if one is already loaded we take that, else the loader's default.
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string error;
+  bool load() {
+    if (handle) return true;
+    handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!handle) { error = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+#define LSB_SYM(field, name)                                            \
+    *reinterpret_cast<void**>(&field) = dlsym(handle, name);           \
+    if (!field) { error = std::string("dlsym ") + name; handle = nullptr; return false; }
+    LSB_SYM(GetUniqueId, "ncclGetUniqueId");
+    LSB_SYM(CommInitRank, "ncclCommInitRank");
+    LSB_SYM(CommDestroy, "ncclCommDestroy");
+    LSB_SYM(AllGather, "ncclAllGather");
+    LSB_SYM(AllReduce, "ncclAllReduce");
+    LSB_SYM(GetErrorString, "ncclGetErrorString");
+#undef LSB_SYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+
+int fail(lsb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_err = msg;
+  return code;
+}
+
+#define CU(c, expr)                                                                          \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess)                                                                   \
+      return fail(c, LSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+  } while (0)
+
+#define NC(c, expr)                                                                          \
+  do {                                                                                       \
+    ncclResult_t r_ = (expr);                                                                \
+    if (r_ != ncclSuccess)                                                                   \
+      return fail(c, LSB_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(r_));  \
+  } while (0)
+
+inline int64_t div_ceil(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+PassPlan plan_pass(const lsb_ctx* c, int digit) {
+  PassPlan p;
+  p.shift = c->cfg.radix_bits * digit;
+  p.bits = std::min<int>(c->cfg.radix_bits, 64 - p.shift);
+  p.lo_bits = p.bits > 8 ? p.bits - 8 : 0;
+  p.hi_bits = p.bits - p.lo_bits;
+  return p;
+}
+
+int phase_mark(lsb_ctx* c, int kind) {
+  if (!(c->cfg.flags & LSB_FLAG_PHASE_EVENTS)) return LSB_OK;
+  cudaEvent_t ev;
+  CU(c, cudaEventCreate(&ev));
+  CU(c, cudaEventRecord(ev, c->stream));
+  c->phase_ev.push_back(ev);
+  c->phase_kind.push_back(kind);
+  return LSB_OK;
+}
+
+int begin_call(lsb_ctx* c) {
+  for (auto ev : c->phase_ev) cudaEventDestroy(ev);
+  c->phase_ev.clear();
+  c->phase_kind.clear();
+  c->launches = 0;
+  c->next_counter = 0;
+  CU(c, cudaMemsetAsync(c->tile_counters, 0, 64 * sizeof(uint32_t), c->stream));
+  CU(c, cudaEventRecord(c->ev_start, c->stream));
+  return phase_mark(c, -1);
+}
+
+int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
+  CU(c, cudaEventRecord(c->ev_stop, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  if (!st) return LSB_OK;
+  memset(st, 0, sizeof(*st));
+  float ms = 0;
+  CU(c, cudaEventElapsedTime(&ms, c->ev_start, c->ev_stop));
+  st->device_ms = ms;
+  st->passes = passes;
+  st->subpasses = subpasses;
+  st->elements = c->here;
+  st->kernel_launches = c->launches;
+  int sp = 0;
+  for (size_t i = 1; i < c->phase_ev.size(); i++) {
+    float d = 0;
+    CU(c, cudaEventElapsedTime(&d, c->phase_ev[i - 1], c->phase_ev[i]));
+    switch (c->phase_kind[i]) {
+      case 0: st->hist_ms += d; break;
+      case 1: st->scan_ms += d; break;
+      case 2:
+        st->partition_ms += d;
+        if (sp < LSB_MAX_SUBPASSES) st->subpass_ms[sp] = d;
+        sp++;
+        break;
+    }
+  }
+  st->partition_launches = subpasses;
+  if (c->G > 1) {
+    CU(c, cudaMemcpy(c->host_small, c->small, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int g = 0; g < c->G; g++) st->sent[g] = (int64_t)c->host_small[g];
+  } else {
+    st->sent[0] = c->here;
+  }
+  return LSB_OK;
+}
+
+// ---- kernel launch helpers -----------------------------------------------------------
+
+int launch_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
+  // hist[] holds nsub 256-bin histograms; more than HIST_MAX_SUB sub-digits => several reads
+  CU(c, cudaMemsetAsync(c->hist, 0, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, c->stream));
+  if (c->here > 0) {
+    HistArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src;
+    a.m = c->here;
+    a.nsub = nsub;
+    for (int s = 0; s < nsub; s++) {
+      a.shift[s] = subs[s].shift;
+      a.mask[s] = (1u << subs[s].bits) - 1;
+    }
+    a.out = c->hist;
+    int grid = (int)std::min<int64_t>(148 * 4, div_ceil(c->here, HIST_THREADS));
+    hist_kernel<<<grid, HIST_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+  }
+  CU(c, cudaGetLastError());
+  int rc = phase_mark(c, 0);
+  if (rc) return rc;
+  scan256_kernel<<<nsub, 256, 0, c->stream>>>(c->hist, c->scan_out);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return phase_mark(c, 1);
+}
+
+int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bits, const int64_t* seg_start,
+                     const uint32_t* seg_tile_start, const int64_t* bases, int dst_buf, bool global_dst) {
+  if (c->gen > 126) {  // tags exhausted: wipe the look-back words and start over
+    CU(c, cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
+    c->gen = 0;
+  }
+  if (c->next_counter >= 64) return fail(c, LSB_ERR_STATE, "too many partition launches in one call");
+  PartArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src = src;
+  a.shift = shift;
+  a.mask = (1u << bits) - 1;
+  a.seg_bits = seg_bits;
+  a.seg_start = seg_start;
+  a.seg_tile_start = seg_tile_start;
+  a.bases = bases;
+  a.lookback = c->lookback;
+  a.tile_counter = c->tile_counters + c->next_counter++;
+  a.tag_agg = (uint64_t)(2 * c->gen + 1) << 56;
+  a.tag_inc = (uint64_t)(2 * c->gen + 2) << 56;
+  c->gen++;
+  if (global_dst) {
+    a.per = c->per;
+    a.world = c->G;
+    for (int g = 0; g < c->G; g++) a.dst[g] = c->peer[dst_buf][g];
+  } else {
+    a.per = INT64_MAX / 16;
+    a.world = 1;
+    a.dst[0] = c->buf[dst_buf];
+  }
+  const int64_t max_tiles = div_ceil(c->here, PT_TILE) + (seg_bits ? (1 << seg_bits) : 0);
+  if (c->here > 0) {
+    partition_kernel<<<(unsigned)max_tiles, PT_THREADS, PT_SMEM, c->stream>>>(a);
+    c->launches++;
+  }
+  CU(c, cudaGetLastError());
+  return phase_mark(c, 2);
+}
+
+// exchange-free barrier across GPUs, ordered on the sort stream
+int stream_barrier(lsb_ctx* c) {
+  if (c->G == 1) return LSB_OK;
+  NC(c, g_nccl.AllReduce(c->small + 32, c->small + 32, 1, ncclUint64, ncclSum, c->comm, c->stream));
+  return LSB_OK;
+}
+
+// counts of a full digit of this shard -> all-gather -> digit-major/rank-minor scan -> mybase[]
+int global_offsets(lsb_ctx* c, int nb) {
+  const unsigned long long* all = c->counts_local;
+  if (c->G > 1) {
+    NC(c, g_nccl.AllGather(c->counts_local, c->counts_all, (size_t)nb, ncclUint64, c->comm, c->stream));
+    all = c->counts_all;
+  }
+  CU(c, cudaMemsetAsync(c->small, 0, 8 * sizeof(unsigned long long), c->stream));
+  GlobalScanArgs s;
+  s.counts = all;
+  s.nb = nb;
+  s.G = c->G;
+  s.my = c->my;
+  s.per = c->per;
+  s.mybase = c->mybase;
+  s.sent = c->small;
+  global_scan_kernel<<<1, 1024, 0, c->stream>>>(s);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return LSB_OK;
+}
+
+// one reference pass, multi-GPU shape (also correct for G == 1)
+int pass_global(lsb_ctx* c, int digit, int* subpasses) {
+  const PassPlan p = plan_pass(c, digit);
+  const int other = c->cur ^ 1;
+  const Elt* src2 = c->buf[c->cur];
+  int dst_buf = other;
+  const int64_t* seg_start = c->one_seg_start;
+  const uint32_t* seg_tiles = c->one_seg_tiles;
+  int rc;
+  if (p.lo_bits > 0) {
+    SubPass lo{p.shift, p.lo_bits};
+    if ((rc = launch_hist(c, c->buf[c->cur], &lo, 1))) return rc;
+    // scan_out[0..256] = segment starts of the shard once grouped by the low bits
+    if ((rc = launch_partition(c, c->buf[c->cur], p.shift, p.lo_bits, 0, c->one_seg_start, c->one_seg_tiles,
+                               c->scan_out, other, false)))
+      return rc;
+    (*subpasses)++;
+    seg_tiles_kernel<<<1, 256, 0, c->stream>>>(c->scan_out, 1 << p.lo_bits, PT_TILE, c->seg_tile_start);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    src2 = c->buf[other];
+    dst_buf = c->cur;
+    seg_start = c->scan_out;
+    seg_tiles = c->seg_tile_start;
+  }
+  const int nb = 1 << p.bits;
+  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
+  if (c->here > 0) {
+    SegCountArgs sc;
+    sc.src = src2;
+    sc.m = c->here;
+    sc.seg_start = seg_start;
+    sc.lo_bits = p.lo_bits;
+    sc.shift_hi = p.shift + p.lo_bits;
+    sc.mask_hi = (1u << p.hi_bits) - 1;
+    sc.out = c->counts_local;
+    int grid = (int)std::min<int64_t>(148 * 4, div_ceil(c->here, HIST_THREADS));
+    seg_count_kernel<<<grid, HIST_THREADS, 0, c->stream>>>(sc);
+    c->launches++;
+    CU(c, cudaGetLastError());
+  }
+  if ((rc = phase_mark(c, 0))) return rc;
+  // the all-gather doubles as the barrier "every GPU is done reading the shard that is
+  // about to be overwritten by its peers"
+  if ((rc = global_offsets(c, nb))) return rc;
+  if ((rc = phase_mark(c, 1))) return rc;
+  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
+                             dst_buf, true)))
+    return rc;
+  (*subpasses)++;
+  // peers' stores into my shard must have landed before anything reads it
+  if ((rc = stream_barrier(c))) return rc;
+  c->cur = dst_buf;
+  return LSB_OK;
+}
+
+// passes [d0, d1) on one GPU: one histogram read for all sub-digits, then the partitions
+int passes_single(lsb_ctx* c, int d0, int d1, int* subpasses) {
+  std::vector<SubPass> subs;
+  for (int d = d0; d < d1; d++) {
+    const PassPlan p = plan_pass(c, d);
+    if (p.lo_bits) subs.push_back({p.shift, p.lo_bits});
+    subs.push_back({p.shift + p.lo_bits, p.hi_bits});
+  }
+  int rc;
+  for (size_t s0 = 0; s0 < subs.size(); s0 += HIST_MAX_SUB) {
+    const int ns = (int)std::min<size_t>(HIST_MAX_SUB, subs.size() - s0);
+    if ((rc = launch_hist(c, c->buf[c->cur], subs.data() + s0, ns))) return rc;
+    for (int s = 0; s < ns; s++) {
+      const SubPass& sp = subs[s0 + s];
+      if ((rc = launch_partition(c, c->buf[c->cur], sp.shift, sp.bits, 0, c->one_seg_start, c->one_seg_tiles,
+                                 c->scan_out + (size_t)s * 257, c->cur ^ 1, false)))
+        return rc;
+      c->cur ^= 1;
+      (*subpasses)++;
+    }
+  }
+  return LSB_OK;
+}
+
+int check_ready(lsb_ctx* c) {
+  if (!c) return LSB_ERR_ARG;
+  if (c->G > 1 && !c->comm_ready) return fail(c, LSB_ERR_STATE, "world_size > 1: call lsb_comm_init first");
+  return LSB_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// C ABI
+// =====================================================================================
+extern "C" {
+
+int lsb_abi_version(void) { return LSB_ABI_VERSION; }
+
+const char* lsb_status_string(int s) {
+  switch (s) {
+    case LSB_OK: return "ok";
+    case LSB_ERR_ARG: return "bad argument";
+    case LSB_ERR_CUDA: return "CUDA error";
+    case LSB_ERR_NCCL: return "NCCL error";
+    case LSB_ERR_STATE: return "wrong state";
+    case LSB_ERR_NOMEM: return "out of memory";
+    case LSB_ERR_VERIFY: return "verification failed";
+  }
+  return "unknown";
+}
+
+const char* lsb_last_error(const lsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
+  if (!out || !cfg) return fail(nullptr, LSB_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n < 0 || cfg->world_size < 1 || cfg->world_size > LSB_MAX_GPUS || cfg->world_rank < 0 ||
+      cfg->world_rank >= cfg->world_size || cfg->radix_bits < 1 || cfg->radix_bits > 16 || cfg->ranks < 0)
+    return fail(nullptr, LSB_ERR_ARG, "bad lsb_config (n >= 0, 1 <= world_size <= 8, 1 <= radix_bits <= 16)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, LSB_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, LSB_ERR_ARG, "device ordinal out of range");
+
+  lsb_ctx* c = new lsb_ctx();
+  c->cfg = *cfg;
+  if (c->cfg.ranks == 0) c->cfg.ranks = cfg->world_size;
+  if (c->cfg.and_draws < 1) c->cfg.and_draws = 1;
+  c->G = cfg->world_size;
+  c->my = cfg->world_rank;
+  c->n = cfg->n;
+  // DistributedArray::create, mpi/mpi_lsbsort.cpp:144-149
+  c->per = std::max<int64_t>(div_ceil(c->n, c->G), 1);
+  c->here = c->per;
+  if (c->per * c->my + c->here > c->n) c->here = c->n - c->per * c->my;
+  if (c->here < 0) c->here = 0;
+  c->first = c->per * c->my;
+  c->per_stream = std::max<int64_t>(div_ceil(c->n, c->cfg.ranks), 1);
+  c->npasses = (64 + c->cfg.radix_bits - 1) / c->cfg.radix_bits;
+
+#define CUC(expr)                                                                        \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      int code_ = (e_ == cudaErrorMemoryAllocation) ? LSB_ERR_NOMEM : LSB_ERR_CUDA;      \
+      fail(nullptr, code_, std::string(#expr) + ": " + cudaGetErrorString(e_));          \
+      lsb_destroy(c);                                                                    \
+      return code_;                                                                      \
+    }                                                                                    \
+  } while (0)
+
+  CUC(cudaSetDevice(cfg->device));
+  CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUC(cudaEventCreate(&c->ev_start));
+  CUC(cudaEventCreate(&c->ev_stop));
+  const size_t shard_bytes = (size_t)std::max<int64_t>(c->per, 1) * sizeof(Elt);
+  CUC(cudaMalloc(&c->buf[0], shard_bytes));
+  CUC(cudaMalloc(&c->buf[1], shard_bytes));
+  c->peer[0][c->my] = c->buf[0];
+  c->peer[1][c->my] = c->buf[1];
+  c->lookback_tiles = (size_t)div_ceil(c->per, PT_TILE) + 256 + 1;
+  CUC(cudaMalloc(&c->lookback, c->lookback_tiles * 256 * sizeof(uint64_t)));
+  CUC(cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
+  CUC(cudaMalloc(&c->tile_counters, 64 * sizeof(uint32_t)));
+  CUC(cudaMalloc(&c->hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB));
+  CUC(cudaMalloc(&c->scan_out, sizeof(int64_t) * 257 * HIST_MAX_SUB));
+  CUC(cudaMalloc(&c->counts_local, sizeof(unsigned long long) * 65536));
+  CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
+  CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
+  CUC(cudaMalloc(&c->seg_tile_start, sizeof(uint32_t) * 257));
+  CUC(cudaMalloc(&c->one_seg_start, sizeof(int64_t) * 2));
+  CUC(cudaMalloc(&c->one_seg_tiles, sizeof(uint32_t) * 2));
+  CUC(cudaMalloc(&c->small, sizeof(unsigned long long) * 64));
+  CUC(cudaMalloc(&c->small_all, sizeof(unsigned long long) * 16 * LSB_MAX_GPUS));
+  CUC(cudaMemsetAsync(c->small, 0, sizeof(unsigned long long) * 64, c->stream));
+  CUC(cudaHostAlloc(&c->host_small, sizeof(unsigned long long) * (16 * LSB_MAX_GPUS + 64), cudaHostAllocDefault));
+  const int64_t seg[2] = {0, c->here};
+  const uint32_t tl[2] = {0, (uint32_t)div_ceil(c->here, PT_TILE)};
+  CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
+  CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
+  CUC(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+  CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+  *out = c;
+  return LSB_OK;
+}
+
+void lsb_destroy(lsb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int b = 0; b < 2; b++)
+    for (int g = 0; g < LSB_MAX_GPUS; g++)
+      if (c->peer_open[b][g]) cudaIpcCloseMemHandle(c->peer[b][g]);
+  if (c->comm) g_nccl.CommDestroy(c->comm);
+  for (auto ev : c->phase_ev) cudaEventDestroy(ev);
+  cudaFree(c->buf[0]);
+  cudaFree(c->buf[1]);
+  cudaFree(c->lookback);
+  cudaFree(c->tile_counters);
+  cudaFree(c->hist);
+  cudaFree(c->scan_out);
+  cudaFree(c->counts_local);
+  cudaFree(c->counts_all);
+  cudaFree(c->mybase);
+  cudaFree(c->seg_tile_start);
+  cudaFree(c->one_seg_start);
+  cudaFree(c->one_seg_tiles);
+  cudaFree(c->small);
+  cudaFree(c->small_all);
+  if (c->host_small) cudaFreeHost(c->host_small);
+  if (c->ev_start) cudaEventDestroy(c->ev_start);
+  if (c->ev_stop) cudaEventDestroy(c->ev_stop);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int lsb_comm_unique_id(void* id_out) {
+  if (!id_out) return LSB_ERR_ARG;
+  static_assert(sizeof(ncclUniqueId) == LSB_COMM_ID_BYTES, "ncclUniqueId size");
+  if (!g_nccl.load()) return fail(nullptr, LSB_ERR_NCCL, g_nccl.error);
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, LSB_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+  memcpy(id_out, &id, sizeof(id));
+  return LSB_OK;
+}
+
+int lsb_comm_init(lsb_ctx* c, const void* id_bytes) {
+  if (!c || !id_bytes) return LSB_ERR_ARG;
+  if (c->G == 1) { c->comm_ready = true; return LSB_OK; }
+  if (c->comm_ready) return fail(c, LSB_ERR_STATE, "communicator already initialised");
+  if (!g_nccl.load()) return fail(c, LSB_ERR_NCCL, g_nccl.error);
+  CU(c, cudaSetDevice(c->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, id_bytes, sizeof(id));
+  NC(c, g_nccl.CommInitRank(&c->comm, c->G, id, c->my));
+  // exchange CUDA IPC handles of both shards through the communicator itself
+  struct Handles { cudaIpcMemHandle_t h[2]; };
+  static_assert(sizeof(Handles) == 128, "ipc handle size");
+  Handles mine;
+  CU(c, cudaIpcGetMemHandle(&mine.h[0], c->buf[0]));
+  CU(c, cudaIpcGetMemHandle(&mine.h[1], c->buf[1]));
+  unsigned char* d_h = nullptr;
+  CU(c, cudaMalloc(&d_h, sizeof(Handles) * (c->G + 1)));
+  CU(c, cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, c->stream));
+  NC(c, g_nccl.AllGather(d_h, d_h + sizeof(Handles), sizeof(Handles), ncclUint8, c->comm, c->stream));
+  std::vector<Handles> all(c->G);
+  CU(c, cudaMemcpyAsync(all.data(), d_h + sizeof(Handles), sizeof(Handles) * c->G, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaFree(d_h));
+  for (int g = 0; g < c->G; g++) {
+    if (g == c->my) continue;
+    for (int b = 0; b < 2; b++) {
+      void* p = nullptr;
+      CU(c, cudaIpcOpenMemHandle(&p, all[g].h[b], cudaIpcMemLazyEnablePeerAccess));
+      c->peer[b][g] = reinterpret_cast<Elt*>(p);
+      c->peer_open[b][g] = true;
+    }
+  }
+  c->comm_ready = true;
+  return LSB_OK;
+}
+
+int lsb_shard_info(const lsb_ctx* c, int64_t* per, int64_t* here, int64_t* first_global) {
+  if (!c) return LSB_ERR_ARG;
+  if (per) *per = c->per;
+  if (here) *here = c->here;
+  if (first_global) *first_global = c->first;
+  return LSB_OK;
+}
+
+int lsb_num_passes(const lsb_ctx* c) { return c ? c->npasses : LSB_ERR_ARG; }
+
+int lsb_digit_bits(const lsb_ctx* c, int digit) {
+  if (!c || digit < 0 || digit >= c->npasses) return LSB_ERR_ARG;
+  return plan_pass(c, digit).bits;
+}
+
+int lsb_generate(lsb_ctx* c) {
+  if (!c) return LSB_ERR_ARG;
+  CU(c, cudaSetDevice(c->cfg.device));
+  c->cur = 0;
+  if (c->here > 0) {
+    GenArgs a;
+    a.dst = c->buf[0];
+    a.first_global = c->first;
+    a.count = c->here;
+    a.per_stream = c->per_stream;
+    a.seed_base = c->cfg.seed_base;
+    a.key_mask = c->cfg.key_mask;
+    a.and_draws = c->cfg.and_draws;
+    u128 m, p;
+    pcg_jump_coeffs((u128)32 * (u128)c->cfg.and_draws, m, p);
+    a.row_mult_hi = (uint64_t)(m >> 64);
+    a.row_mult_lo = (uint64_t)m;
+    a.row_plus_hi = (uint64_t)(p >> 64);
+    a.row_plus_lo = (uint64_t)p;
+    const int64_t warps = div_ceil(c->here, 32 * GEN_ROWS);
+    const int64_t blocks = div_ceil(warps * 32, GEN_THREADS);
+    generate_kernel<<<(unsigned)blocks, GEN_THREADS, 0, c->stream>>>(a);
+    CU(c, cudaGetLastError());
+  }
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+int lsb_upload(lsb_ctx* c, const lsb_elt* host, int64_t off, int64_t count) {
+  if (!c || (!host && count) || off < 0 || count < 0 || off + count > c->per) return fail(c, LSB_ERR_ARG, "lsb_upload: range");
+  CU(c, cudaSetDevice(c->cfg.device));
+  if (count) CU(c, cudaMemcpyAsync(c->buf[c->cur] + off, host, (size_t)count * sizeof(Elt), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+int lsb_download(lsb_ctx* c, lsb_elt* host, int64_t off, int64_t count) {
+  if (!c || (!host && count) || off < 0 || count < 0 || off + count > c->per) return fail(c, LSB_ERR_ARG, "lsb_download: range");
+  CU(c, cudaSetDevice(c->cfg.device));
+  if (count) CU(c, cudaMemcpyAsync(host, c->buf[c->cur] + off, (size_t)count * sizeof(Elt), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+int lsb_device_ptr(lsb_ctx* c, void** ptr) {
+  if (!c || !ptr) return LSB_ERR_ARG;
+  *ptr = c->buf[c->cur];
+  return LSB_OK;
+}
+
+int lsb_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return LSB_ERR_ARG;
+  cudaError_t e = cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault);
+  if (e != cudaSuccess) return fail(nullptr, LSB_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  return LSB_OK;
+}
+
+int lsb_host_free(void* ptr) {
+  if (!ptr) return LSB_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? LSB_OK : LSB_ERR_CUDA;
+}
+
+int lsb_sort(lsb_ctx* c, lsb_stats* st) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->cfg.device));
+  if ((rc = begin_call(c))) return rc;
+  int subpasses = 0;
+  if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) {
+    if ((rc = passes_single(c, 0, c->npasses, &subpasses))) return rc;
+  } else {
+    for (int d = 0; d < c->npasses; d++)
+      if ((rc = pass_global(c, d, &subpasses))) return rc;
+  }
+  return end_call(c, st, c->npasses, subpasses);
+}
+
+int lsb_pass(lsb_ctx* c, int digit, lsb_stats* st) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_pass: digit out of range");
+  CU(c, cudaSetDevice(c->cfg.device));
+  if ((rc = begin_call(c))) return rc;
+  int subpasses = 0;
+  if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) rc = passes_single(c, digit, digit + 1, &subpasses);
+  else rc = pass_global(c, digit, &subpasses);
+  if (rc) return rc;
+  return end_call(c, st, 1, subpasses);
+}
+
+int lsb_sort_host(lsb_ctx* c, const lsb_elt* host_in, lsb_elt* host_out, int64_t count, lsb_stats* st) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (count != c->here || (count && (!host_in || !host_out))) return fail(c, LSB_ERR_ARG, "lsb_sort_host: count must equal this shard's size");
+  CU(c, cudaSetDevice(c->cfg.device));
+  c->cur = 0;
+  if (count) CU(c, cudaMemcpyAsync(c->buf[0], host_in, (size_t)count * sizeof(Elt), cudaMemcpyHostToDevice, c->stream));
+  if ((rc = lsb_sort(c, st))) return rc;
+  if (count) CU(c, cudaMemcpyAsync(host_out, c->buf[c->cur], (size_t)count * sizeof(Elt), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+static int dense_counts(lsb_ctx* c, int digit, int* nb_out) {
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits;
+  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
+  if (c->here > 0) {
+    dense_count_kernel<<<148 * 8, 256, 0, c->stream>>>(c->buf[c->cur], c->here, p.shift, (uint32_t)(nb - 1), c->counts_local);
+    CU(c, cudaGetLastError());
+  }
+  *nb_out = nb;
+  return LSB_OK;
+}
+
+int lsb_histogram(lsb_ctx* c, int digit, int64_t* host_counts) {
+  if (!c || !host_counts || digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_histogram: argument");
+  CU(c, cudaSetDevice(c->cfg.device));
+  int nb = 0, rc = dense_counts(c, digit, &nb);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(host_counts, c->counts_local, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+int lsb_starts(lsb_ctx* c, int digit, int64_t* host_starts) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!host_starts || digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_starts: argument");
+  CU(c, cudaSetDevice(c->cfg.device));
+  int nb = 0;
+  if ((rc = dense_counts(c, digit, &nb))) return rc;
+  if ((rc = global_offsets(c, nb))) return rc;
+  CU(c, cudaMemcpyAsync(host_starts, c->mybase, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
+static int local_verify(lsb_ctx* c) {
+  // small[40..44] = checksum[4], violations
+  CU(c, cudaMemsetAsync(c->small + 40, 0, 8 * sizeof(unsigned long long), c->stream));
+  if (c->here > 0) {
+    int grid = (int)std::min<int64_t>(148 * 8, div_ceil(c->here, 256));
+    verify_kernel<<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->here, c->small + 40);
+    CU(c, cudaGetLastError());
+  }
+  return LSB_OK;
+}
+
+int lsb_checksum(lsb_ctx* c, uint64_t out[4]) {
+  if (!c || !out) return LSB_ERR_ARG;
+  CU(c, cudaSetDevice(c->cfg.device));
+  int rc = local_verify(c);
+  if (rc) return rc;
+  CU(c, cudaMemcpyAsync(c->host_small, c->small + 40, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 4; i++) out[i] = c->host_small[i];
+  return LSB_OK;
+}
+
+int lsb_verify_device(lsb_ctx* c, lsb_verify* out) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  if (!out) return LSB_ERR_ARG;
+  CU(c, cudaSetDevice(c->cfg.device));
+  if ((rc = local_verify(c))) return rc;
+  // record = {checksum[4], violations, here, first.key, first.val, last.key, last.val}
+  unsigned long long* rec = c->small + 48;  // 10 words used, 16 reserved
+  CU(c, cudaMemcpyAsync(rec, c->small + 40, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+  const unsigned long long here = (unsigned long long)c->here;
+  CU(c, cudaMemcpyAsync(rec + 5, &here, sizeof(here), cudaMemcpyHostToDevice, c->stream));
+  if (c->here > 0) {
+    CU(c, cudaMemcpyAsync(rec + 6, c->buf[c->cur], sizeof(Elt), cudaMemcpyDeviceToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(rec + 8, c->buf[c->cur] + (c->here - 1), sizeof(Elt), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  const unsigned long long* all = rec;
+  if (c->G > 1) {
+    NC(c, g_nccl.AllGather(rec, c->small_all, 16, ncclUint64, c->comm, c->stream));
+    all = c->small_all;
+  }
+  CU(c, cudaMemcpyAsync(c->host_small, all, sizeof(unsigned long long) * 16 * c->G, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  memset(out, 0, sizeof(*out));
+  bool have_prev = false;
+  uint64_t pk = 0, pv = 0;
+  for (int g = 0; g < c->G; g++) {
+    const unsigned long long* r = c->host_small + 16 * g;
+    out->checksum[0] += r[0];
+    out->checksum[1] ^= r[1];
+    out->checksum[2] ^= r[2];
+    out->checksum[3] += r[3];
+    out->order_violations += (int64_t)r[4];
+    out->elements += (int64_t)r[5];
+    if (r[5] == 0) continue;
+    if (have_prev && (pk > r[6] || (pk == r[6] && pv >= r[7]))) out->order_violations++;
+    pk = r[8];
+    pv = r[9];
+    have_prev = true;
+  }
+  if (out->order_violations) return fail(c, LSB_ERR_VERIFY, "shards are not strictly increasing in (key,val)");
+  return LSB_OK;
+}
+
+}  // extern "C"

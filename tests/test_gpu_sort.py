@@ -1,0 +1,190 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle -- needs a B200."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import distributed_lsb_b200 as lsb  # noqa: E402
+from distributed_lsb_b200 import lsbsort as L  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+ALL = 0xFFFFFFFFFFFFFFFF
+
+
+def _golden(golden_dir):
+    with open(os.path.join(golden_dir, "survey_vectors.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("n,R,mask,k", [
+    (1, 1, ALL, 1), (100, 4, ALL, 1), (100, 3, ALL, 1), (10, 8, ALL, 1), (2049, 2, ALL, 1),
+    (1 << 20, 4, ALL, 1), ((1 << 20) + 77, 7, ALL, 1), (300000, 4, 0xFFFFFF, 1), (200000, 3, ALL, 3),
+])
+def test_generate_matches_oracle(n, R, mask, k):
+    # bit-exact: the pcg64(rank) fill loop, mpi/mpi_lsbsort.cpp:650-656
+    with lsb.DistributedSorter(n, ranks=R, key_mask=mask, and_draws=k) as s:
+        s.generate()
+        got = s.download()
+    want = O.generate(n, R, key_mask=mask, and_draws=k)[:n]
+    assert (got == want).all()
+
+
+@pytest.mark.parametrize("n,R", [(0, 1), (1, 1), (1, 4), (3, 4), (7, 3), (10, 8), (100, 4), (4095, 2), (4096, 1),
+                                 (4097, 2), (65536, 4), (65537, 4), (1 << 20, 4), ((1 << 21) + 12345, 8)])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+def test_sort_matches_oracle(n, R, flags):
+    with lsb.DistributedSorter(n, ranks=R, flags=flags) as s:
+        s.generate()
+        st = s.my_sort()
+        got = s.download()
+    want = O.sort(O.generate(n, R), n, R)
+    assert st.passes == 4
+    assert (got == want).all()  # bit-exact, keys and stable values
+
+
+def test_config0_2pow24_r4_golden(golden_dir):
+    """BASELINE configs[0]: mpirun -n 4, n = 2^24, --verify"""
+    v = next(r for r in _golden(golden_dir)["sort"] if r["n"] == 1 << 24 and r["ranks"] == 4)
+    n, R = 1 << 24, 4
+    with lsb.DistributedSorter(n, ranks=R) as s:
+        s.generate()
+        g = s.download()
+        assert f"{O.fnv1a64(g):016x}" == v["fnv_in"]
+        s.my_sort()
+        out = s.download()
+        s.verify()
+    assert f"{O.fnv1a64(out):016x}" == v["fnv_out"]
+    assert [f"{int(out['key'][0]):016x}", int(out["val"][0])] == v["first"]
+    assert [f"{int(out['key'][n - 1]):016x}", int(out["val"][n - 1])] == v["last"]
+    assert (out == O.sort(g, n, R)).all()
+
+
+@pytest.mark.parametrize("bits", [4, 8, 11, 13, 16])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+def test_radix_widths(golden_dir, bits, flags):
+    # config 5: digit width changes the pass count, never the answer
+    final = _golden(golden_dir)["radix_n1048576_r4"]["final"]
+    n, R = 1 << 20, 4
+    with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, flags=flags) as s:
+        assert s.num_passes() == -(-64 // bits)
+        s.generate()
+        st = s.my_sort()
+        out = s.download()
+    assert st.passes == -(-64 // bits)
+    assert f"{O.fnv1a64(out):016x}" == final
+
+
+@pytest.mark.parametrize("bits", [8, 11, 16])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+def test_each_pass_matches_reference_pass(golden_dir, bits, flags):
+    """globalShuffle pass by pass: counts (:226-229), starts (:350,:407-413), array after (:546-575)"""
+    gold = _golden(golden_dir)
+    n, R = 1 << 20, 4
+    a = O.generate(n, R)[:n]
+    with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, flags=flags) as s:
+        s.generate()
+        for p in range(s.num_passes()):
+            want, counts, starts, _ = O.one_pass(a, n, 1, bits, p)  # one shard == one rank
+            assert (s.histogram(p) == counts[0]).all()
+            assert (s.starts(p) == starts[:, 0]).all()
+            st = s.global_shuffle(p)
+            assert st.passes == 1
+            a = s.download()
+            assert (a == want).all(), f"pass {p}"
+            if bits == 16:
+                assert f"{O.fnv1a64(a):016x}" == gold["passes_n1048576_r4_radix16"][p]["fnv_after"]
+
+
+@pytest.mark.parametrize("mask,k", [(0xFFFFFF, 1), (ALL, 3), (0xFF, 1), (0, 1), (0xFFFF0000FFFF, 2)])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+def test_skewed_keys_stable(mask, k, flags):
+    # config 4: single-bin digits, massive ties; stability decides the answer
+    n, R = 700001, 4
+    with lsb.DistributedSorter(n, ranks=R, key_mask=mask, and_draws=k, flags=flags) as s:
+        s.generate()
+        before = s.checksum()
+        s.my_sort()
+        out = s.download()
+        v = s.verify()
+    g = O.generate(n, R, key_mask=mask, and_draws=k)
+    assert before == O.checksum(g[:n])
+    assert (out == O.sort(g, n, R)).all()
+    assert list(v.checksum) == before and v.order_violations == 0 and v.elements == n
+
+
+def test_uploaded_data_and_host_path():
+    # caller-supplied records (the reference only sorts generated data): duplicates + arbitrary vals
+    rng = np.random.default_rng(5)
+    n = 250001
+    a = np.zeros(n, dtype=lsb.ELT)
+    a["key"] = rng.integers(0, 1 << 20, n, dtype=np.uint64) << np.uint64(13)
+    a["val"] = np.arange(n, dtype=np.uint64)
+    want = O.stable_sort(a, n)
+    with lsb.DistributedSorter(n) as s:
+        s.upload(a)
+        s.my_sort()
+        assert (s.download() == want).all()
+        out = np.empty_like(a)
+        st = s.sort_host(a, out)
+        assert (out == want).all() and st.elements == n
+
+
+def test_verifier_rejects_unsorted_and_unstable():
+    n = 100000
+    with lsb.DistributedSorter(n) as s:
+        s.generate()
+        v = s.verify(raise_on_failure=False)
+        assert v.order_violations > 0
+        s.my_sort()
+        good = s.download()
+        s.verify()
+        bad = good.copy()
+        bad[[10, 11]] = bad[[11, 10]]
+        s.upload(bad)
+        assert s.verify(raise_on_failure=False).order_violations == 2
+        tie = good.copy()
+        tie["key"][500] = tie["key"][499]
+        tie["val"][500] = tie["val"][499]  # equal (key,val): not strictly increasing
+        s.upload(tie)
+        with pytest.raises(lsb.LsbError):
+            s.verify()
+
+
+def test_repeated_sorts_reuse_context():
+    # look-back words are tagged by generation instead of being cleared: exercise the wrap
+    n = 50000
+    want = O.sort(O.generate(n, 2), n, 2)
+    with lsb.DistributedSorter(n, ranks=2, radix_bits=8) as s:
+        for _ in range(20):  # 160 partition launches > 127 tags
+            s.generate()
+            s.my_sort()
+        assert (s.download() == want).all()
+
+
+@pytest.mark.parametrize("n", [1 << 26, 1 << 28])
+def test_large_properties(n):
+    # sizes with no CPU oracle: strictly increasing (key,val) + same multiset == stable sort
+    with lsb.DistributedSorter(n, ranks=1) as s:
+        s.generate()
+        before = s.checksum()
+        assert before[3] == (n * (n - 1) // 2) % (1 << 64)
+        st = s.my_sort()
+        v = s.verify()
+        assert list(v.checksum) == before and v.elements == n
+        # idempotence: sorting sorted data changes nothing
+        s.my_sort()
+        assert list(s.verify().checksum) == before
+    assert st.subpasses == 8
+
+
+def test_errors_are_reported_not_swallowed():
+    with pytest.raises(lsb.LsbError):
+        lsb.DistributedSorter(10, radix_bits=17)
+    with pytest.raises(lsb.LsbError):
+        lsb.DistributedSorter(10, world_size=2, world_rank=2)
+    with lsb.DistributedSorter(10, world_size=2, world_rank=0) as s:
+        with pytest.raises(lsb.LsbError):
+            s.my_sort()  # communicator not initialised
