@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: M 16-byte elements sorted / s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU
+
+A "step" is one full mySort (all passes) over one freshly generated synthetic input.
+  N = 1 : BASELINE configs[1] -- single B200, n = 2^30 uniform pcg64 keys, 16-bit digits.
+  N > 1 : BASELINE configs[2] weak scaling -- 2^31 elements per GPU, R = N pcg64 streams.
+`value` is device time (CUDA events on the sort stream, inputs already in HBM, max over ranks);
+`e2e` is the same metric through the host-buffer C-ABI call lsb_sort_host (pinned host memory
+in, pinned host memory out, copies inside the timed region, wall clock).
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "M 16-byte elements sorted/s"
+UNIT = "M elements/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled while the timed region runs"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the UNMODIFIED mpi_lsbsort.cpp (oracle/_ref, ranks = threads)
+# --------------------------------------------------------------------------------------
+def run_reference_once(n, ranks):
+    from oracle import oracle as O  # the one place bench.py may execute oracle/: the CPU baseline
+    if not os.path.exists(O.REF_BIN):
+        O.build()
+    env = dict(os.environ, SHIM_RANKS=str(ranks))
+    out = subprocess.run([O.REF_BIN, "--n", str(n), "--no-verify"], env=env, check=True, capture_output=True,
+                         text=True).stdout
+    m = re.search(r"That's ([0-9.eE+-]+) M elements sorted / s", out)
+    s = re.search(r"Sorted \d+ values in ([0-9.eE+-]+)", out)
+    return float(m.group(1)), float(s.group(1))
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(sample_log2=None):
+    """bounded sample of the same workload on the host cores; ~10-30 s of CPU work"""
+    cores = host_threads()
+    ranks = max(1, min(cores, 64))
+    n = 1 << (sample_log2 or 24)
+    rate, secs = run_reference_once(n, ranks)
+    if sample_log2 is None and secs < 1.5:  # fast host: take a bigger, steadier sample
+        n = 1 << 26
+        rate, secs = run_reference_once(n, ranks)
+    return {"value": rate, "unit": UNIT, "cores": ranks, "kind": "reference",
+            "sample": f"unmodified mpi/mpi_lsbsort.cpp over the ranks-as-threads mpi.h shim (oracle/_ref), "
+                      f"{ranks} ranks, n=2^{n.bit_length() - 1} --no-verify, {secs:.2f} s sort time"}
+
+
+def main_reference(args, rank):
+    if rank != 0:
+        return 0
+    cores = host_threads()
+    ranks = max(1, min(cores, 64))
+    n = 1 << args.ref_log2
+    for _ in range(args.warmup and 1):
+        run_reference_once(n, ranks)
+    rates, secs = [], []
+    for _ in range(args.steps):
+        r, s = run_reference_once(n, ranks)
+        rates.append(r)
+        secs.append(s)
+    value = n * len(secs) / sum(secs) / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": f"n=2^{args.ref_log2} per step on the host CPU",
+                   "radix_bits": 16},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ranks, "kind": "reference",
+                         "sample": f"unmodified mpi/mpi_lsbsort.cpp via oracle/_ref (shim transport), {ranks} ranks, "
+                                   f"n=2^{args.ref_log2} --no-verify per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(gpus):
+    if gpus == 1:
+        return "configs[1]: single B200, 2^30 uniform-random 16-byte elements, 16-bit digits (4 passes)"
+    return f"configs[2] weak scaling: {gpus}xB200, 2^31 16-byte elements per GPU, 16-bit digits (4 passes)"
+
+
+# --------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------
+def main_cuda(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import distributed_lsb_b200 as lsb
+    from distributed_lsb_b200 import lsbsort as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    per_gpu_log2 = args.log2n if args.log2n else (30 if world == 1 else 31)
+    n = world << per_gpu_log2
+    sorter = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=local_rank,
+                                   radix_bits=args.radix, flags=L.FLAG_PHASE_EVENTS if args.phases else 0)
+    if world > 1:
+        ids = [lsb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sorter.comm_init(ids[0])
+
+    # ---- warm-up (also the correctness gate: a wrong sort is not a benchmark) ----
+    for w in range(args.warmup):
+        sorter.generate()
+        before = sorter.checksum() if w == 0 else None
+        sorter.my_sort()
+        if w == 0:
+            v = sorter.verify()
+            if world == 1 and list(v.checksum) != before:
+                raise SystemExit("bench.py: multiset hash changed across the sort")
+
+    # ---- timed: exactly K steps, device time per step, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    step_ms, launches, part_ms, part_launches = [], 0, 0.0, 0
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.steps):
+        sorter.generate()          # fresh input, resident in HBM before the timed region
+        barrier()
+        st = sorter.my_sort()      # CUDA events bracket the kernels on the sort stream
+        barrier()
+        step_ms.append(max_over_ranks(st.device_ms))
+        launches += st.kernel_launches
+        part_ms += st.partition_ms
+        part_launches += st.partition_launches
+    clocks = sampler.stop() if rank == 0 else None
+    total_s = sum(step_ms) / 1e3
+    value = n * args.steps / total_s / 1e6
+
+    # ---- per-kernel durations for the roofline (phase events; separate, untimed-for-value step) ----
+    sorter.close()
+    sorter = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=local_rank,
+                                   radix_bits=args.radix, flags=L.FLAG_PHASE_EVENTS)
+    if world > 1:
+        ids = [lsb.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sorter.comm_init(ids[0])
+    kp_ms, kp_n, hist_ms = [], 0, []
+    for _ in range(max(2, min(args.steps, 3))):
+        sorter.generate()
+        barrier()
+        st = sorter.my_sort()
+        kp_ms.append(st.partition_ms / max(st.partition_launches, 1))
+        kp_n = st.partition_launches
+        hist_ms.append(st.hist_ms)
+    peak, peak_src = _peaks()
+    here = sorter.here
+    launch_ms = statistics.mean(kp_ms)
+    achieved = here * 32 / (launch_ms * 1e-3) / 1e9
+    npass = sorter.num_passes()
+    sort_ms = statistics.mean(step_ms)
+    pass_achieved = here * 32 * npass / (sort_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    # ---- end to end through the host-buffer C-ABI entry point ----
+    e2e = None
+    if not args.no_e2e:
+        sorter.generate()
+        hin, hout = L.PinnedBuffer(here), L.PinnedBuffer(here)
+        sorter.download(out=hin.array)
+        walls = []
+        for i in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            sorter.sort_host(hin.array, hout.array)
+            barrier()
+            if i:  # first one is warm-up
+                walls.append(max_over_ranks(time.perf_counter() - t0))
+        ok = bool((hout.array["key"][:-1] <= hout.array["key"][1:]).all()) if here < (1 << 27) else \
+            bool((hout.array["key"][:1 << 20][:-1] <= hout.array["key"][:1 << 20][1:]).all())
+        e2e = {"value": n / statistics.mean(walls) / 1e6, "unit": UNIT, "h2d_bytes_per_step": here * 16 * world,
+               "d2h_bytes_per_step": here * 16 * world, "ms_per_step": 1e3 * statistics.mean(walls),
+               "api": "lsb_sort_host (pinned host in/out)", "output_sorted": ok}
+        hin.free()
+        hout.free()
+    sorter.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sort_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(world), "n_total": n, "n_per_gpu": here, "radix_bits": args.radix,
+                       "passes": npass, "pcg_streams": world,
+                       "l2": "inputs (16-32 GiB per GPU) are far larger than the 126 MB L2; no flush needed"},
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "lsb::partition_kernel (one 8-bit stable counting-sort step)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": here * 32, "launch_ms": launch_ms,
+                         "launches_per_sort": kp_n,
+                         "note": "a launch reads and writes every 16-byte element once (32 B/elem); a 16-bit "
+                                 "reference pass takes two launches, see pass_roofline"},
+            "pass_roofline": {"bound": "hbm" if world == 1 else "nvlink",
+                              "algorithmic_bytes_per_sort": here * 32 * npass, "achieved": pass_achieved,
+                              "peak": peak, "unit": "GB/s", "frac": pass_achieved / peak,
+                              "note": "SURVEY 8(d): 32 B per element per reference pass over the whole sort time "
+                                      "(histogram + all partition launches)"},
+            "hist_ms_per_sort": statistics.mean(hist_ms),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--log2n", type=int, default=0, help="log2 elements per GPU (default 30 at N=1, 31 at N>1)")
+    ap.add_argument("--radix", type=int, default=16)
+    ap.add_argument("--phases", action="store_true", help="record per-kernel events inside the timed steps too")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-log2", type=int, default=24, help="--impl reference: log2 of the per-step sample")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1 and args.impl == "cuda":
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return main_reference(args, rank)
+    return main_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
