@@ -372,18 +372,32 @@ __global__ void __launch_bounds__(1024) global_scan_kernel(const GlobalScanArgs 
 // GLOBAL output index, and the 16-byte store goes straight into the destination GPU's
 // shard (peer pointer over NVLink) -- no 24-byte ShuffleBufSortElement, no staging.
 //
-// Shape: tiles of PT_TILE elements taken in input order (dynamic tile id), ranks inside
-// the tile from warp match_any + warp-private shared histograms, cross-tile offsets per
-// bin by decoupled look-back over 64-bit {tag, count} words, tile re-ordered through
-// shared memory so that every bin's run leaves as consecutive 16-byte vector stores.
+// Shape (one CTA = one tile of PT_TILE elements, taken in input order by a dynamic tile id):
+//   1. the tile is pulled into shared memory by ONE bulk async copy (cp.async.bulk, TMA
+//      engine, mbarrier completion): no registers hold elements, so 5 CTAs fit per SM and
+//      their load / rank / look-back / store phases overlap each other;
+//   2. early counts: per-warp 256-bin histograms (packed u16, shared atomics) -> tile totals
+//      are published for the decoupled look-back before the ranking starts;
+//   3. stable ranks: per 32-element row, peers = 8 ballots, running per-warp offsets in
+//      shared memory; the rank is written as a 2-byte permutation entry perm[slot] = index;
+//   4. decoupled look-back over 64-bit {tag, count} words gives each bin's offset among
+//      earlier tiles (the tag is a per-launch generation, so the words are never cleared);
+//   5. slot p of the tile gathers raw[perm[p]] from shared memory: consecutive threads write
+//      consecutive 16-byte slots of a bin's run in the destination shard.
 // The input may be split into segments (already grouped by the low sub-digit); a tile never
 // straddles a segment, look-back restarts at each segment, and bin bases are per segment.
 // ------------------------------------------------------------------------------------
-constexpr int PT_THREADS = 512;
+constexpr int PT_THREADS = 256;
 constexpr int PT_WARPS = PT_THREADS / 32;
 constexpr int PT_IPT = 8;
-constexpr int PT_TILE = PT_THREADS * PT_IPT;  // 4096 elements = 64 KiB
-constexpr int PT_SMEM = PT_TILE * 16 + PT_WARPS * 256 * 4 + 256 * 4 + 256 * 8;
+constexpr int PT_TILE = PT_THREADS * PT_IPT;  // 2048 elements = 32 KiB
+constexpr int PT_CTAS_PER_SM = 5;
+// raw tile | perm (u16) | per-warp histograms (u16) | bin -> destination offset (i64)
+constexpr int PT_SMEM_RAW = 0;
+constexpr int PT_SMEM_PERM = PT_SMEM_RAW + PT_TILE * 16;
+constexpr int PT_SMEM_WHIST = PT_SMEM_PERM + PT_TILE * 2;
+constexpr int PT_SMEM_BINDST = PT_SMEM_WHIST + PT_WARPS * 256 * 2;
+constexpr int PT_SMEM = PT_SMEM_BINDST + 256 * 8;
 
 constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
 
@@ -405,123 +419,164 @@ struct PartArgs {
   Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
 };
 
-__global__ void __launch_bounds__(PT_THREADS, 2) partition_kernel(const PartArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  Elt* s_sorted = reinterpret_cast<Elt*>(smem);
-  unsigned* s_whist = reinterpret_cast<unsigned*>(smem + PT_TILE * 16);
-  unsigned* s_binstart = s_whist + PT_WARPS * 256;
-  long long* s_bindst = reinterpret_cast<long long*>(s_binstart + 256);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "LSB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra LSB_DONE;\n\t"
+      "bra LSB_WAIT;\n\t"
+      "LSB_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy on the TMA engine; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// lanes of `vmask` whose 8-bit `bin` equals mine (8 ballots; match.any measured ~10x slower here)
+__device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
+  unsigned peers = vmask;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (bin >> b) & 1u;
+    const unsigned bal = __ballot_sync(vmask, bit);
+    peers &= bit ? bal : ~bal;
+  }
+  return peers;
+}
+
+__global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(const PartArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Elt* s_raw = reinterpret_cast<Elt*>(smem + PT_SMEM_RAW);
+  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + PT_SMEM_PERM);
+  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + PT_SMEM_WHIST);
+  long long* s_bindst = reinterpret_cast<long long*>(smem + PT_SMEM_BINDST);
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ int s_tile, s_seg, s_count, s_first;
-  __shared__ long long s_begin;
-  __shared__ unsigned s_wtot[8];
+  __shared__ unsigned s_wtot[PT_WARPS];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nseg = 1 << a.seg_bits;
 
   if (tid == 0) {
-    const unsigned tile = atomicAdd(a.tile_counter, 1u);
-    const int nseg = 1 << a.seg_bits;
-    if (tile >= a.seg_tile_start[nseg]) {
-      s_tile = -1;
-    } else {
-      int lo = 0, hi = nseg;  // last segment whose first tile is <= tile
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (a.seg_tile_start[mid] <= tile) lo = mid; else hi = mid;
-      }
-      const unsigned t_in = tile - a.seg_tile_start[lo];
-      const long long begin = a.seg_start[lo] + (long long)t_in * PT_TILE;
-      const long long end = a.seg_start[lo + 1];
-      s_tile = (int)tile;
-      s_seg = lo;
-      s_begin = begin;
-      s_count = (int)((end - begin < PT_TILE) ? (end - begin) : PT_TILE);
-      s_first = (t_in == 0);
-    }
+    mbar_init(&s_bar, 1);
+    const unsigned t = atomicAdd(a.tile_counter, 1u);
+    s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
+    s_seg = 0;
   }
-  for (int i = tid; i < PT_WARPS * 256; i += PT_THREADS) s_whist[i] = 0;
+  // zero the packed per-warp histograms (PT_WARPS*256 u16 = 1024 u32)
+  for (int i = tid; i < PT_WARPS * 128; i += PT_THREADS) reinterpret_cast<unsigned*>(s_whist)[i] = 0;
   __syncthreads();
   const int tile = s_tile;
   if (tile < 0) return;
+  // which segment owns this tile: the one with first_tile <= tile < next first_tile
+  if (nseg > 1 && tid < nseg) {
+    const unsigned f = a.seg_tile_start[tid], l = a.seg_tile_start[tid + 1];
+    if (f <= (unsigned)tile && (unsigned)tile < l) s_seg = tid;
+  }
+  if (nseg > 1) __syncthreads();
+  if (tid == 0) {
+    const int sg = s_seg;
+    const unsigned t_in = (unsigned)tile - a.seg_tile_start[sg];
+    const long long begin = a.seg_start[sg] + (long long)t_in * PT_TILE;
+    const long long left = a.seg_start[sg + 1] - begin;
+    const int cnt = (int)(left < PT_TILE ? left : PT_TILE);
+    s_count = cnt;
+    s_first = (t_in == 0);
+    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
+    bulk_load(s_raw, a.src + begin, (unsigned)cnt * 16u, &s_bar);
+  }
+  __syncthreads();
   const int count = s_count;
   const int seg = s_seg;
+  const bool first = s_first;
+  mbar_wait(&s_bar, 0);
 
-  // ---- load: warp-striped, PT_IPT independent 16-byte loads in flight per thread ----
-  Elt e[PT_IPT];
+  // ---- bins of my 8 elements (warp-striped rows), early per-warp counts ----
   const int idx0 = warp * (32 * PT_IPT) + lane;
-  {
-    const Elt* src = a.src + s_begin + idx0;
-#pragma unroll
-    for (int j = 0; j < PT_IPT; j++) {
-      if (idx0 + j * 32 < count) e[j] = ld_stream(src + j * 32);
-      else { e[j].key = 0; e[j].val = 0; }
-    }
-  }
-
-  // ---- rank inside the warp, in input order (stable) ----
-  unsigned* wh = s_whist + warp * 256;
-  unsigned rank[PT_IPT];
-  const unsigned lt = lanemask_lt();
+  unsigned bins[PT_IPT];
+  unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
 #pragma unroll
   for (int j = 0; j < PT_IPT; j++) {
-    const bool valid = idx0 + j * 32 < count;
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    rank[j] = 0;
-    if (valid) {
-      const unsigned bin = (unsigned)(e[j].key >> a.shift) & a.mask;
-      const unsigned peers = __match_any_sync(vmask, bin);
-      const unsigned old = wh[bin];
-      __syncwarp(vmask);
-      if ((peers & lt) == 0) wh[bin] = old + __popc(peers);
-      __syncwarp(vmask);
-      rank[j] = old + __popc(peers & lt);
+    const int idx = idx0 + j * 32;
+    bins[j] = 0xffffffffu;
+    if (idx < count) {
+      const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
+      bins[j] = bin;
+      atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
     }
   }
   __syncthreads();
 
-  // ---- per-bin: exclusive over warps, tile total, publish aggregate early ----
-  unsigned tile_count = 0;
-  uint64_t* my_state = nullptr;
-  if (tid < 256) {
+  // ---- per bin: tile total (published at once), exclusive over warps, start inside the tile ----
+  unsigned tile_count = 0, binstart = 0;
+  uint64_t* my_state = a.lookback + (size_t)tile * 256 + tid;
+  {
+    unsigned wc[PT_WARPS];
 #pragma unroll
     for (int w = 0; w < PT_WARPS; w++) {
-      const unsigned c = s_whist[w * 256 + tid];
-      s_whist[w * 256 + tid] = tile_count;
-      tile_count += c;
+      wc[w] = s_whist[w * 256 + tid];
+      tile_count += wc[w];
     }
-    my_state = a.lookback + (size_t)tile * 256 + tid;
-    st_relaxed_gpu(my_state, (s_first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
-    // exclusive scan of tile totals over the 256 bins
+    st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
     unsigned incl = tile_count;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += o;
     }
     if (lane == 31) s_wtot[warp] = incl;
-    s_binstart[tid] = incl - tile_count;  // exclusive inside the warp; warp offset added below
-  }
-  __syncthreads();
-  if (tid < 256) {
-    unsigned off = 0;
-    for (int i = 0; i < warp; i++) off += s_wtot[i];
-    s_binstart[tid] += off;
+    __syncthreads();
+    binstart = incl - tile_count;
+    for (int i = 0; i < warp; i++) binstart += s_wtot[i];
+    unsigned run = binstart;
+#pragma unroll
+    for (int w = 0; w < PT_WARPS; w++) {
+      s_whist[w * 256 + tid] = (unsigned short)run;
+      run += wc[w];
+    }
   }
   __syncthreads();
 
-  // ---- reorder the tile through shared memory ----
+  // ---- stable ranks: slot of each element inside the tile, written as a permutation ----
+  {
+    unsigned short* wh = s_whist + warp * 256;
+    const unsigned lt = lanemask_lt();
 #pragma unroll
-  for (int j = 0; j < PT_IPT; j++) {
-    if (idx0 + j * 32 < count) {
-      const unsigned bin = (unsigned)(e[j].key >> a.shift) & a.mask;
-      const unsigned p = s_binstart[bin] + wh[bin] + rank[j];
-      s_sorted[p] = e[j];
+    for (int j = 0; j < PT_IPT; j++) {
+      const int idx = idx0 + j * 32;
+      const bool valid = idx < count;
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const unsigned bin = bins[j];
+        const unsigned peers = match_bin(vmask, bin);
+        const unsigned old = wh[bin];
+        __syncwarp(vmask);
+        if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+        __syncwarp(vmask);
+        s_perm[old + __popc(peers & lt)] = (unsigned short)idx;
+      }
     }
   }
 
   // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
-  if (tid < 256) {
+  {
     uint64_t excl = 0;
-    if (!s_first) {
+    if (!first) {
       int look = tile - 1;
       while (true) {
         const uint64_t v = ld_relaxed_gpu(a.lookback + (size_t)look * 256 + tid);
@@ -532,7 +587,7 @@ __global__ void __launch_bounds__(PT_THREADS, 2) partition_kernel(const PartArgs
       }
       st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
     }
-    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)s_binstart[tid];
+    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)binstart;
   }
   __syncthreads();
 
@@ -541,9 +596,9 @@ __global__ void __launch_bounds__(PT_THREADS, 2) partition_kernel(const PartArgs
   for (int k = 0; k < PT_IPT; k++) {
     const int p = k * PT_THREADS + tid;
     if (p < count) {
-      const Elt el = s_sorted[p];
+      const Elt el = s_raw[s_perm[p]];
       const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
-      long long g = s_bindst[bin] + p;
+      const long long g = s_bindst[bin] + p;
       Elt* out;
       if (a.world == 1) {
         out = a.dst[0] + g;

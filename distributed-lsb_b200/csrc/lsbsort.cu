@@ -479,6 +479,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
   CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
   CUC(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
+  CUC(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
