@@ -372,10 +372,10 @@ __global__ void __launch_bounds__(1024) global_scan_kernel(const GlobalScanArgs 
 // GLOBAL output index, and the 16-byte store goes straight into the destination GPU's
 // shard (peer pointer over NVLink) -- no 24-byte ShuffleBufSortElement, no staging.
 //
-// Shape (one CTA = one tile of PT_TILE elements, taken in input order by a dynamic tile id):
+// Shape (one CTA = one tile of TILE elements, taken in input order by a dynamic tile id):
 //   1. the tile is pulled into shared memory by ONE bulk async copy (cp.async.bulk, TMA
-//      engine, mbarrier completion): no registers hold elements, so 5 CTAs fit per SM and
-//      their load / rank / look-back / store phases overlap each other;
+//      engine, mbarrier completion): no registers hold elements, so several CTAs fit per SM
+//      and their load / rank / look-back / store phases overlap each other;
 //   2. early counts: per-warp 256-bin histograms (packed u16, shared atomics) -> tile totals
 //      are published for the decoupled look-back before the ranking starts;
 //   3. stable ranks: per 32-element row, peers = 8 ballots, running per-warp offsets in
@@ -387,19 +387,23 @@ __global__ void __launch_bounds__(1024) global_scan_kernel(const GlobalScanArgs 
 // The input may be split into segments (already grouped by the low sub-digit); a tile never
 // straddles a segment, look-back restarts at each segment, and bin bases are per segment.
 // ------------------------------------------------------------------------------------
-constexpr int PT_THREADS = 256;
-constexpr int PT_WARPS = PT_THREADS / 32;
-constexpr int PT_IPT = 8;
-constexpr int PT_TILE = PT_THREADS * PT_IPT;  // 2048 elements = 32 KiB
-constexpr int PT_CTAS_PER_SM = 5;
-// raw tile | perm (u16) | per-warp histograms (u16) | bin -> destination offset (i64)
-constexpr int PT_SMEM_RAW = 0;
-constexpr int PT_SMEM_PERM = PT_SMEM_RAW + PT_TILE * 16;
-constexpr int PT_SMEM_WHIST = PT_SMEM_PERM + PT_TILE * 2;
-constexpr int PT_SMEM_BINDST = PT_SMEM_WHIST + PT_WARPS * 256 * 2;
-constexpr int PT_SMEM = PT_SMEM_BINDST + 256 * 8;
-
+constexpr int PT_LB_WINDOW = 4;
 constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
+
+template <int THREADS_, int IPT_, int MINB_>
+struct PartCfg {
+  static constexpr int THREADS = THREADS_;
+  static constexpr int WARPS = THREADS_ / 32;
+  static constexpr int IPT = IPT_;
+  static constexpr int MINB = MINB_;
+  static constexpr int TILE = THREADS_ * IPT_;
+  // raw tile | perm (u16) | per-warp histograms (u16) | bin -> destination offset (i64)
+  static constexpr int SMEM_RAW = 0;
+  static constexpr int SMEM_PERM = SMEM_RAW + TILE * 16;
+  static constexpr int SMEM_WHIST = SMEM_PERM + TILE * 2;
+  static constexpr int SMEM_BINDST = SMEM_WHIST + WARPS * 256 * 2;
+  static constexpr int SMEM = SMEM_BINDST + 256 * 8;
+};
 
 struct PartArgs {
   const Elt* src;
@@ -447,74 +451,41 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                : "memory");
 }
 
-// lanes of `vmask` whose 8-bit `bin` equals mine (8 ballots; match.any measured ~10x slower here)
+// lanes of `vmask` whose 8-bit `bin` equals mine: 8 ballots (match.any measured ~10x slower:
+// its cost grows with the number of distinct values, and a row of 32 bins is mostly distinct)
 __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
   unsigned peers = vmask;
 #pragma unroll
   for (int b = 0; b < 8; b++) {
-    const bool bit = (bin >> b) & 1u;
+    // per bit: bit test -> predicate, ballot, select 0 / ~0 on the same predicate, and-xor
+    const bool bit = (bin & (1u << b)) != 0;
     const unsigned bal = __ballot_sync(vmask, bit);
-    peers &= bit ? bal : ~bal;
+    peers &= bal ^ (bit ? 0u : 0xffffffffu);
   }
   return peers;
 }
 
-__global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(const PartArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  Elt* s_raw = reinterpret_cast<Elt*>(smem + PT_SMEM_RAW);
-  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + PT_SMEM_PERM);
-  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + PT_SMEM_WHIST);
-  long long* s_bindst = reinterpret_cast<long long*>(smem + PT_SMEM_BINDST);
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tile, s_seg, s_count, s_first;
-  __shared__ unsigned s_wtot[PT_WARPS];
-
+template <class C, bool FULL>
+__device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
+                                               unsigned* s_wtot, int tile, int seg, int count, bool first,
+                                               int first_tile) {
+  Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
+  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
+  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
+  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nseg = 1 << a.seg_bits;
 
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    const unsigned t = atomicAdd(a.tile_counter, 1u);
-    s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
-    s_seg = 0;
-  }
-  // zero the packed per-warp histograms (PT_WARPS*256 u16 = 1024 u32)
-  for (int i = tid; i < PT_WARPS * 128; i += PT_THREADS) reinterpret_cast<unsigned*>(s_whist)[i] = 0;
-  __syncthreads();
-  const int tile = s_tile;
-  if (tile < 0) return;
-  // which segment owns this tile: the one with first_tile <= tile < next first_tile
-  if (nseg > 1 && tid < nseg) {
-    const unsigned f = a.seg_tile_start[tid], l = a.seg_tile_start[tid + 1];
-    if (f <= (unsigned)tile && (unsigned)tile < l) s_seg = tid;
-  }
-  if (nseg > 1) __syncthreads();
-  if (tid == 0) {
-    const int sg = s_seg;
-    const unsigned t_in = (unsigned)tile - a.seg_tile_start[sg];
-    const long long begin = a.seg_start[sg] + (long long)t_in * PT_TILE;
-    const long long left = a.seg_start[sg + 1] - begin;
-    const int cnt = (int)(left < PT_TILE ? left : PT_TILE);
-    s_count = cnt;
-    s_first = (t_in == 0);
-    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
-    bulk_load(s_raw, a.src + begin, (unsigned)cnt * 16u, &s_bar);
-  }
-  __syncthreads();
-  const int count = s_count;
-  const int seg = s_seg;
-  const bool first = s_first;
-  mbar_wait(&s_bar, 0);
+  mbar_wait(s_bar, 0);
 
-  // ---- bins of my 8 elements (warp-striped rows), early per-warp counts ----
-  const int idx0 = warp * (32 * PT_IPT) + lane;
-  unsigned bins[PT_IPT];
+  // ---- bins of my elements (warp-striped rows), early per-warp counts ----
+  const int idx0 = warp * (32 * C::IPT) + lane;
+  unsigned bins[C::IPT];
   unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
 #pragma unroll
-  for (int j = 0; j < PT_IPT; j++) {
+  for (int j = 0; j < C::IPT; j++) {
     const int idx = idx0 + j * 32;
-    bins[j] = 0xffffffffu;
-    if (idx < count) {
+    bins[j] = 0;
+    if (FULL || idx < count) {
       const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
       bins[j] = bin;
       atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
@@ -524,11 +495,12 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
 
   // ---- per bin: tile total (published at once), exclusive over warps, start inside the tile ----
   unsigned tile_count = 0, binstart = 0;
-  uint64_t* my_state = a.lookback + (size_t)tile * 256 + tid;
-  {
-    unsigned wc[PT_WARPS];
+  uint64_t* my_state = nullptr;
+  if (tid < 256) {
+    my_state = a.lookback + (size_t)tile * 256 + tid;
+    unsigned wc[C::WARPS];
 #pragma unroll
-    for (int w = 0; w < PT_WARPS; w++) {
+    for (int w = 0; w < C::WARPS; w++) {
       wc[w] = s_whist[w * 256 + tid];
       tile_count += wc[w];
     }
@@ -540,12 +512,12 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
       if (lane >= d) incl += o;
     }
     if (lane == 31) s_wtot[warp] = incl;
-    __syncthreads();
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // only the 8 scanning warps
     binstart = incl - tile_count;
     for (int i = 0; i < warp; i++) binstart += s_wtot[i];
     unsigned run = binstart;
 #pragma unroll
-    for (int w = 0; w < PT_WARPS; w++) {
+    for (int w = 0; w < C::WARPS; w++) {
       s_whist[w * 256 + tid] = (unsigned short)run;
       run += wc[w];
     }
@@ -557,10 +529,10 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
     unsigned short* wh = s_whist + warp * 256;
     const unsigned lt = lanemask_lt();
 #pragma unroll
-    for (int j = 0; j < PT_IPT; j++) {
+    for (int j = 0; j < C::IPT; j++) {
       const int idx = idx0 + j * 32;
-      const bool valid = idx < count;
-      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      const bool valid = FULL || idx < count;
+      const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
       if (valid) {
         const unsigned bin = bins[j];
         const unsigned peers = match_bin(vmask, bin);
@@ -574,16 +546,31 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
   }
 
   // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
-  {
+  // A window of PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles
+  // in flight the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
+  if (tid < 256) {
     uint64_t excl = 0;
     if (!first) {
       int look = tile - 1;
-      while (true) {
-        const uint64_t v = ld_relaxed_gpu(a.lookback + (size_t)look * 256 + tid);
-        const uint64_t tag = v & ~LB_VALUE_MASK;
-        if (tag == a.tag_inc) { excl += v & LB_VALUE_MASK; break; }
-        if (tag == a.tag_agg) { excl += v & LB_VALUE_MASK; look--; continue; }
-        __nanosleep(20);
+      bool done = false;
+      while (!done) {
+        uint64_t v[PT_LB_WINDOW];
+#pragma unroll
+        for (int i = 0; i < PT_LB_WINDOW; i++) {
+          const int t = look - i;
+          v[i] = (t >= first_tile) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
+        }
+        int used = 0;
+#pragma unroll
+        for (int i = 0; i < PT_LB_WINDOW; i++) {
+          if (!done && used == i) {
+            const uint64_t tag = v[i] & ~LB_VALUE_MASK;
+            if (tag == a.tag_inc) { excl += v[i] & LB_VALUE_MASK; done = true; }
+            else if (tag == a.tag_agg) { excl += v[i] & LB_VALUE_MASK; used = i + 1; }
+          }
+        }
+        look -= used;
+        if (!done && used == 0) __nanosleep(20);
       }
       st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
     }
@@ -593,9 +580,9 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
 
   // ---- write: consecutive threads -> consecutive slots of a bin's run ----
 #pragma unroll
-  for (int k = 0; k < PT_IPT; k++) {
-    const int p = k * PT_THREADS + tid;
-    if (p < count) {
+  for (int k = 0; k < C::IPT; k++) {
+    const int p = k * C::THREADS + tid;
+    if (FULL || p < count) {
       const Elt el = s_raw[s_perm[p]];
       const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
       const long long g = s_bindst[bin] + p;
@@ -611,6 +598,62 @@ __global__ void __launch_bounds__(PT_THREADS, PT_CTAS_PER_SM) partition_kernel(c
     }
   }
 }
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile, s_seg, s_count, s_first, s_first_tile;
+  __shared__ unsigned s_wtot[8];
+
+  const int tid = threadIdx.x;
+  const int nseg = 1 << a.seg_bits;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const unsigned t = atomicAdd(a.tile_counter, 1u);
+    s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
+    s_seg = 0;
+  }
+  // zero the packed per-warp histograms (WARPS*256 u16)
+  for (int i = tid; i < C::WARPS * 128; i += C::THREADS)
+    reinterpret_cast<unsigned*>(smem + C::SMEM_WHIST)[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile < 0) return;
+  // which segment owns this tile: the one with first_tile <= tile < next first_tile
+  if (nseg > 1) {
+    if (tid < nseg) {
+      const unsigned f = a.seg_tile_start[tid], l = a.seg_tile_start[tid + 1];
+      if (f <= (unsigned)tile && (unsigned)tile < l) s_seg = tid;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int sg = s_seg;
+    const unsigned t_in = (unsigned)tile - a.seg_tile_start[sg];
+    const long long begin = a.seg_start[sg] + (long long)t_in * C::TILE;
+    const long long left = a.seg_start[sg + 1] - begin;
+    const int cnt = (int)(left < C::TILE ? left : C::TILE);
+    s_count = cnt;
+    s_first = (t_in == 0);
+    s_first_tile = (int)a.seg_tile_start[sg];
+    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
+    bulk_load(smem + C::SMEM_RAW, a.src + begin, (unsigned)cnt * 16u, &s_bar);
+  }
+  __syncthreads();
+  const int count = s_count;
+  if (count == C::TILE)
+    partition_tile<C, true>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+  else
+    partition_tile<C, false>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+}
+
+// tile shapes: {threads, elements per thread, CTAs per SM}; all need nseg <= THREADS
+typedef PartCfg<256, 8, 5> PartCfgA;   // 2048-element tiles, 43 KiB, 40 warps/SM
+typedef PartCfg<512, 8, 2> PartCfgB;   // 4096-element tiles, 82 KiB, 32 warps/SM
+typedef PartCfg<384, 8, 3> PartCfgC;   // 3072-element tiles, 62 KiB, 36 warps/SM
+typedef PartCfg<512, 10, 2> PartCfgD;  // 5120-element tiles, 100 KiB, 32 warps/SM
 
 // ------------------------------------------------------------------------------------
 // verification: strictly increasing (key,val) + multiset hash (mpi/mpi_lsbsort.cpp:710-739)

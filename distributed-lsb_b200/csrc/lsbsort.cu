@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,6 +60,8 @@ struct lsb_ctx {
   uint32_t* tile_counters = nullptr;  // [64]
   int next_counter = 0;
   int gen = 0;
+  int variant = 0;   // partition tile shape (PartCfgA..D), LSB_PT_VARIANT
+  int tile = 0;      // elements per partition tile
   unsigned long long* hist = nullptr;        // [HIST_MAX_SUB][256]
   int64_t* scan_out = nullptr;               // [HIST_MAX_SUB][257]
   unsigned long long* counts_local = nullptr;  // [65536]
@@ -262,9 +265,14 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
     a.world = 1;
     a.dst[0] = c->buf[dst_buf];
   }
-  const int64_t max_tiles = div_ceil(c->here, PT_TILE) + (seg_bits ? (1 << seg_bits) : 0);
+  const int64_t max_tiles = div_ceil(c->here, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
   if (c->here > 0) {
-    partition_kernel<<<(unsigned)max_tiles, PT_THREADS, PT_SMEM, c->stream>>>(a);
+    switch (c->variant) {
+      case 1: partition_kernel<PartCfgB><<<(unsigned)max_tiles, PartCfgB::THREADS, PartCfgB::SMEM, c->stream>>>(a); break;
+      case 2: partition_kernel<PartCfgC><<<(unsigned)max_tiles, PartCfgC::THREADS, PartCfgC::SMEM, c->stream>>>(a); break;
+      case 3: partition_kernel<PartCfgD><<<(unsigned)max_tiles, PartCfgD::THREADS, PartCfgD::SMEM, c->stream>>>(a); break;
+      default: partition_kernel<PartCfgA><<<(unsigned)max_tiles, PartCfgA::THREADS, PartCfgA::SMEM, c->stream>>>(a); break;
+    }
     c->launches++;
   }
   CU(c, cudaGetLastError());
@@ -317,7 +325,7 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
                                c->scan_out, other, false)))
       return rc;
     (*subpasses)++;
-    seg_tiles_kernel<<<1, 256, 0, c->stream>>>(c->scan_out, 1 << p.lo_bits, PT_TILE, c->seg_tile_start);
+    seg_tiles_kernel<<<1, 256, 0, c->stream>>>(c->scan_out, 1 << p.lo_bits, c->tile, c->seg_tile_start);
     c->launches++;
     CU(c, cudaGetLastError());
     src2 = c->buf[other];
@@ -458,7 +466,14 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->buf[1], shard_bytes));
   c->peer[0][c->my] = c->buf[0];
   c->peer[1][c->my] = c->buf[1];
-  c->lookback_tiles = (size_t)div_ceil(c->per, PT_TILE) + 256 + 1;
+  {
+    const char* v = getenv("LSB_PT_VARIANT");
+    c->variant = v ? atoi(v) : 3;  // PartCfgD measured fastest on B200 (profiles/)
+    if (c->variant < 0 || c->variant > 3) c->variant = 3;
+    const int tiles[4] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE};
+    c->tile = tiles[c->variant];
+  }
+  c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
   CUC(cudaMalloc(&c->lookback, c->lookback_tiles * 256 * sizeof(uint64_t)));
   CUC(cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
   CUC(cudaMalloc(&c->tile_counters, 64 * sizeof(uint32_t)));
@@ -475,11 +490,17 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMemsetAsync(c->small, 0, sizeof(unsigned long long) * 64, c->stream));
   CUC(cudaHostAlloc(&c->host_small, sizeof(unsigned long long) * (16 * LSB_MAX_GPUS + 64), cudaHostAllocDefault));
   const int64_t seg[2] = {0, c->here};
-  const uint32_t tl[2] = {0, (uint32_t)div_ceil(c->here, PT_TILE)};
+  const uint32_t tl[2] = {0, (uint32_t)div_ceil(c->here, c->tile)};
   CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
   CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
-  CUC(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM));
-  CUC(cudaFuncSetAttribute(partition_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define LSB_SET_ATTR(CFG)                                                                                   \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM)); \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  LSB_SET_ATTR(PartCfgA)
+  LSB_SET_ATTR(PartCfgB)
+  LSB_SET_ATTR(PartCfgC)
+  LSB_SET_ATTR(PartCfgD)
+#undef LSB_SET_ATTR
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
