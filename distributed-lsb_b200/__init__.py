@@ -7,6 +7,7 @@ through the alias module at the repository root:
 
     import distributed_lsb_b200 as lsb
 """
+from . import hostlogic  # noqa: F401
 from .lsbsort import (  # noqa: F401
     ELT,
     DistributedSorter,

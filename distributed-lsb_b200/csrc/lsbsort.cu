@@ -584,6 +584,15 @@ int lsb_comm_init(lsb_ctx* c, const void* id_bytes) {
   return LSB_OK;
 }
 
+int lsb_barrier(lsb_ctx* c) {
+  int rc = check_ready(c);
+  if (rc) return rc;
+  CU(c, cudaSetDevice(c->cfg.device));
+  if ((rc = stream_barrier(c))) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return LSB_OK;
+}
+
 int lsb_shard_info(const lsb_ctx* c, int64_t* per, int64_t* here, int64_t* first_global) {
   if (!c) return LSB_ERR_ARG;
   if (per) *per = c->per;

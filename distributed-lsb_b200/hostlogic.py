@@ -1,0 +1,90 @@
+"""Host-side index arithmetic of the distributed sort, as plain integer/numpy functions.
+
+These restate, for the host (planning, reporting, tests), what the kernels do on the device:
+the block distribution of DistributedArray (mpi/mpi_lsbsort.cpp:109-120,144-149), the split of a
+digit into sub-digits, the digit-major / rank-minor exclusive scan (:350,:385-414) and the
+send-count matrix (:553-554).  Nothing here is on the sort's data path.
+"""
+import numpy as np
+
+
+def div_ceil(a, b):
+    return (a + b - 1) // b
+
+
+def per_rank(n, ranks):
+    """numElementsPerRank: ceil(n / ranks) (:144)"""
+    return max(div_ceil(n, ranks), 1)
+
+
+def elements_here(n, ranks, r):
+    """numElementsHere with the reference's clamping (:145-149)"""
+    per = per_rank(n, ranks)
+    return max(min(per, n - per * r), 0)
+
+
+def local_to_global(per, rank, loc):
+    return rank * per + loc  # localIdxToGlobalIdx (:109-111)
+
+
+def global_to_local(per, glb):
+    rank = glb // per  # globalIdxToLocalIdx (:113-120)
+    return rank, glb - rank * per
+
+
+def num_passes(radix_bits):
+    return div_ceil(64, radix_bits)  # N_DIGITS (:22), ceil as chpl/arkouda-radix-sort.chpl:78-79
+
+
+def plan_pass(radix_bits, digit):
+    """(shift, bits, lo_bits, hi_bits) of reference pass `digit`: a digit wider than 8 bits is
+    sorted as a stable low-sub-digit step followed by a stable high-sub-digit step"""
+    shift = radix_bits * digit
+    bits = min(radix_bits, 64 - shift)
+    lo = bits - 8 if bits > 8 else 0
+    return shift, bits, lo, bits - lo
+
+
+def subpasses(radix_bits):
+    out = []
+    for d in range(num_passes(radix_bits)):
+        shift, _, lo, hi = plan_pass(radix_bits, d)
+        if lo:
+            out.append((shift, lo))
+        out.append((shift + lo, hi))
+    return out
+
+
+def global_starts(counts):
+    """counts[rank][digit] -> starts[digit][rank]: exclusive scan in digit-major, rank-minor
+    order, i.e. GlobalStarts[digit * R + rank] (:350,:407-413)"""
+    counts = np.asarray(counts, dtype=np.int64)
+    flat = counts.T.reshape(-1)
+    starts = np.cumsum(flat) - flat
+    return starts.reshape(counts.shape[1], counts.shape[0])
+
+
+def send_counts(counts, per):
+    """sendcounts[src][dst]: elements rank src sends to rank dst (:553-554), from counts alone"""
+    counts = np.asarray(counts, dtype=np.int64)
+    R = counts.shape[0]
+    starts = global_starts(counts)
+    out = np.zeros((R, R), dtype=np.int64)
+    for r in range(R):
+        b = starts[:, r]
+        e = b + counts[r]
+        for dst in range(R):
+            lo, hi = dst * per, (dst + 1) * per
+            out[r, dst] = np.clip(np.minimum(e, hi) - np.maximum(b, lo), 0, None).sum()
+    return out
+
+
+def remote_fraction(sent_row, me):
+    """share of a shard's elements that leave the GPU in a pass (NVLink term of the roofline)"""
+    total = int(sum(sent_row))
+    return 0.0 if total == 0 else 1.0 - int(sent_row[me]) / total
+
+
+def pass_roofline_ms(m, f_remote, hbm_gbs, nvlink_gbs):
+    """t_pass >= max(m*32 B / BW_hbm, m*16 B*f_remote / BW_nvlink)"""
+    return max(m * 32 / (hbm_gbs * 1e9), m * 16 * f_remote / (nvlink_gbs * 1e9)) * 1e3

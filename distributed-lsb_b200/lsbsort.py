@@ -88,6 +88,7 @@ def load_library():
     L.lsb_status_string.restype = ctypes.c_char_p
     L.lsb_comm_unique_id.argtypes = [vp]
     L.lsb_comm_init.argtypes = [vp, vp]
+    L.lsb_barrier.argtypes = [vp]
     L.lsb_shard_info.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(i64), ctypes.POINTER(i64)]
     L.lsb_generate.argtypes = [vp]
     L.lsb_upload.argtypes = [vp, vp, i64, i64]
@@ -198,6 +199,10 @@ class DistributedSorter:
     def comm_init(self, unique_id):
         _prefer_torch_nccl()
         self._check(self._L.lsb_comm_init(self._ctx, unique_id), "lsb_comm_init")
+
+    def barrier(self):
+        """MPI_Barrier(MPI_COMM_WORLD): all GPUs drained their sort streams"""
+        self._check(self._L.lsb_barrier(self._ctx), "lsb_barrier")
 
     # -- data ---------------------------------------------------------------------------
     def generate(self):

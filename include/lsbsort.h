@@ -129,6 +129,10 @@ const char* lsb_status_string(int status);
 int lsb_comm_unique_id(void* id_out /* LSB_COMM_ID_BYTES */);
 int lsb_comm_init(lsb_ctx* ctx, const void* id /* LSB_COMM_ID_BYTES */);
 
+/* MPI_Barrier(MPI_COMM_WORLD) (:688,:693): every GPU has finished everything queued on
+ * its sort stream.  Collective; a plain device synchronise when G == 1. */
+int lsb_barrier(lsb_ctx* ctx);
+
 /* ---- data ---------------------------------------------------------------------- */
 
 /* per = numElementsPerRank (:103), here = numElementsHere (:104), first = r*per */

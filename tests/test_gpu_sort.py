@@ -190,3 +190,50 @@ def test_errors_are_reported_not_swallowed():
     with lsb.DistributedSorter(10, world_size=2, world_rank=0) as s:
         with pytest.raises(lsb.LsbError):
             s.my_sort()  # communicator not initialised
+
+
+def _run_driver(*args):
+    import subprocess
+    exe = os.path.join(os.path.dirname(lsb.library_path()), "driver", "lsbsort")
+    if not os.path.exists(exe):
+        pytest.skip("driver not built")
+    r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+    return r.returncode, r.stdout
+
+
+@pytest.mark.parametrize("R,n", [(1, 10), (1, 100), (4, 100), (3, 100), (4, 1 << 20)])
+def test_cpp_driver_prints_what_the_reference_prints(golden_dir, R, n):
+    """same knobs, same report lines (mpi/mpi_lsbsort.cpp:619-620,646,662,684,697-699,712) and the
+    same A[...] lines as the unmodified reference's --print for the slots both programs show"""
+    import re
+    with open(os.path.join(golden_dir, "ref_print.json")) as f:
+        case = next(c for c in json.load(f)["cases"] if c["ranks"] == R and c["n"] == n)
+    rc, out = _run_driver("--n", str(n), "--ranks", str(R), "--print", "--verify")
+    assert rc == 0, out
+    lines = out.splitlines()
+    assert lines[0] == f"Total number of MPI ranks: {R}" and lines[1] == f"Problem size: {n}"
+    for must in ("Generating random values", "Sorting", "Verifying"):
+        assert must in lines
+    assert any(re.match(r"Generated random values in \S+ s$", l) for l in lines)
+    assert any(re.match(rf"Sorted {n} values in \S+$", l) for l in lines)
+    assert any(re.match(r"That's \S+ M elements sorted / s$", l) for l in lines)
+    blocks, cur = [], None
+    for l in lines:
+        if l.startswith("A: displaying"):
+            cur = {}
+            blocks.append(cur)
+        m = re.match(r"A\[(\d+)\] = \(([0-9a-f]{16}),(\d+)\)$", l)
+        if m and cur is not None:
+            cur[int(m.group(1))] = (m.group(2), int(m.group(3)))
+    assert len(blocks) == 2 and len(blocks[0]) == min(10, n)
+    for blk, ref in ((blocks[0], case["before"]), (blocks[1], case["after"])):
+        refd = {i: (k, v) for i, k, v in ref}
+        for i, kv in blk.items():
+            assert refd[i] == kv, (i, kv, refd[i])
+
+
+def test_cpp_driver_exit_code_and_knobs():
+    rc, out = _run_driver("--n", "300000", "--radix", "11", "--key-mask", "0xFFFFFF", "--verify")
+    assert rc == 0 and "Verifying" in out and "Verification FAILED" not in out
+    rc, out = _run_driver("--n", "1000", "--no-verify")
+    assert rc == 0 and "Verifying" not in out
