@@ -175,9 +175,38 @@ __device__ __forceinline__ void smem_count(unsigned* hist, unsigned bin, unsigne
 // One read of the shard produces the 256-bin histograms of up to 16 sub-digits (every
 // sub-pass of a single-GPU sort): block-private shared-memory histograms, coalesced
 // 8-byte key loads with 4 loads in flight per thread, one global atomic per bin per CTA.
+// NSUB is a compile-time count so the per-key loop is fully unrolled with shifts and masks
+// in registers; BYTES = the sub-digits are exactly bytes 0..NSUB-1 of the key (radix 8/16).
+// Skew: when the whole warp agrees on the key's upper 32 bits (keys with few random bits),
+// the sub-digits that live there are counted by one lane (+32) instead of a 32-way
+// same-address atomic.
+template <int NSUB, bool BYTES>
+__device__ __forceinline__ void hist_key(unsigned* sh, uint64_t k, const int* shift, const unsigned* mask,
+                                         unsigned active) {
+  const unsigned hi = (unsigned)(k >> 32);
+  const bool hi_uniform = __all_sync(active, hi == __shfl_sync(active, hi, __ffs(active) - 1));
+  const bool leader = (threadIdx.x & 31) == (__ffs(active) - 1);
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) {
+    const int sh_s = BYTES ? 8 * s : shift[s];
+    const unsigned bin = BYTES ? (unsigned)(k >> (8 * s)) & 255u : (unsigned)(k >> sh_s) & mask[s];
+    const bool in_hi = BYTES ? (s >= 4) : (sh_s >= 32);
+    if (in_hi && hi_uniform) {
+      if (leader) atomicAdd(sh + s * 256 + bin, (unsigned)__popc(active));
+    } else {
+      atomicAdd(sh + s * 256 + bin, 1u);
+    }
+  }
+}
+
+template <int NSUB, bool BYTES>
 __global__ void __launch_bounds__(HIST_THREADS) hist_kernel(const HistArgs a) {
-  __shared__ unsigned sh[HIST_MAX_SUB * 256];
-  for (int i = threadIdx.x; i < a.nsub * 256; i += HIST_THREADS) sh[i] = 0;
+  __shared__ unsigned sh[NSUB * 256];
+  for (int i = threadIdx.x; i < NSUB * 256; i += HIST_THREADS) sh[i] = 0;
+  int shift[NSUB];
+  unsigned mask[NSUB];
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) { shift[s] = a.shift[s]; mask[s] = a.mask[s]; }
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * HIST_THREADS;
   int64_t i = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
@@ -187,17 +216,14 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_kernel(const HistArgs a) {
 #pragma unroll
     for (int u = 0; u < U; u++) k[u] = ld_stream_key(a.src + i + u * stride);
 #pragma unroll
-    for (int u = 0; u < U; u++)
-      for (int s = 0; s < a.nsub; s++)
-        smem_count(sh + s * 256, (unsigned)(k[u] >> a.shift[s]) & a.mask[s], 0xffffffffu);
+    for (int u = 0; u < U; u++) hist_key<NSUB, BYTES>(sh, k[u], shift, mask, 0xffffffffu);
   }
   for (; i < a.m; i += stride) {
-    unsigned active = __activemask();
-    uint64_t k = ld_stream_key(a.src + i);
-    for (int s = 0; s < a.nsub; s++) smem_count(sh + s * 256, (unsigned)(k >> a.shift[s]) & a.mask[s], active);
+    const unsigned active = __activemask();
+    hist_key<NSUB, BYTES>(sh, ld_stream_key(a.src + i), shift, mask, active);
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < a.nsub * 256; j += HIST_THREADS)
+  for (int j = threadIdx.x; j < NSUB * 256; j += HIST_THREADS)
     if (sh[j]) atomicAdd(a.out + j, (unsigned long long)sh[j]);
 }
 
@@ -453,14 +479,34 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
 
 // lanes of `vmask` whose 8-bit `bin` equals mine: 8 ballots (match.any measured ~10x slower:
 // its cost grows with the number of distinct values, and a row of 32 bins is mostly distinct)
+template <bool FULL>
 __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
+  // (hardware match.any, whole or per nibble, measured 30-40 % slower: its cost grows with the
+  // number of distinct values in the warp, and a row of 32 bins is mostly distinct)
   unsigned peers = vmask;
+  if (FULL) {
 #pragma unroll
-  for (int b = 0; b < 8; b++) {
-    // per bit: bit test -> predicate, ballot, select 0 / ~0 on the same predicate, and-xor
-    const bool bit = (bin & (1u << b)) != 0;
-    const unsigned bal = __ballot_sync(vmask, bit);
-    peers &= bal ^ (bit ? 0u : 0xffffffffu);
+    for (int b = 0; b < 8; b++) {
+      // 4 SASS instructions per bit (the C++ form below compiles to 6-7): bit test -> predicate,
+      // ballot, select 0 / ~0 on the same predicate, peers &= ballot ^ select
+      unsigned bal;
+      asm("{\n\t.reg .pred p;\n\t.reg .b32 t, m;\n\t"
+          "and.b32 t, %2, %3;\n\t"
+          "setp.ne.u32 p, t, 0;\n\t"
+          "vote.sync.ballot.b32 %1, p, 0xffffffff;\n\t"
+          "selp.b32 m, 0, -1, p;\n\t"
+          "lop3.b32 %0, %0, %1, m, 0x60;\n\t}"
+          : "+r"(peers), "=r"(bal)
+          : "r"(bin), "r"(1u << b));
+      (void)bal;
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const bool bit = (bin & (1u << b)) != 0;
+      const unsigned bal = __ballot_sync(vmask, bit);
+      peers &= bal ^ (bit ? 0u : 0xffffffffu);
+    }
   }
   return peers;
 }
@@ -535,7 +581,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
       if (valid) {
         const unsigned bin = bins[j];
-        const unsigned peers = match_bin(vmask, bin);
+        const unsigned peers = match_bin<FULL>(vmask, bin);
         const unsigned old = wh[bin];
         __syncwarp(vmask);
         if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
@@ -654,6 +700,8 @@ typedef PartCfg<256, 8, 5> PartCfgA;   // 2048-element tiles, 43 KiB, 40 warps/S
 typedef PartCfg<512, 8, 2> PartCfgB;   // 4096-element tiles, 82 KiB, 32 warps/SM
 typedef PartCfg<384, 8, 3> PartCfgC;   // 3072-element tiles, 62 KiB, 36 warps/SM
 typedef PartCfg<512, 10, 2> PartCfgD;  // 5120-element tiles, 100 KiB, 32 warps/SM
+typedef PartCfg<512, 11, 2> PartCfgE;  // 5632-element tiles, 109 KiB, 32 warps/SM
+typedef PartCfg<640, 8, 2> PartCfgF;   // 5120-element tiles, 102 KiB, 40 warps/SM
 
 // ------------------------------------------------------------------------------------
 // verification: strictly increasing (key,val) + multiset hash (mpi/mpi_lsbsort.cpp:710-739)

@@ -223,7 +223,29 @@ int launch_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
     }
     a.out = c->hist;
     int grid = (int)std::min<int64_t>(148 * 4, div_ceil(c->here, HIST_THREADS));
-    hist_kernel<<<grid, HIST_THREADS, 0, c->stream>>>(a);
+    bool bytes = true;  // sub-digits are exactly bytes 0..nsub-1 of the key (radix 8 and 16)
+    for (int s = 0; s < nsub; s++) bytes = bytes && subs[s].shift == 8 * s && subs[s].bits == 8;
+#define LSB_HIST(N, B) hist_kernel<N, B><<<grid, HIST_THREADS, 0, c->stream>>>(a)
+    if (bytes && nsub == 8) LSB_HIST(8, true);
+    else switch (nsub) {
+      case 1: LSB_HIST(1, false); break;
+      case 2: LSB_HIST(2, false); break;
+      case 3: LSB_HIST(3, false); break;
+      case 4: LSB_HIST(4, false); break;
+      case 5: LSB_HIST(5, false); break;
+      case 6: LSB_HIST(6, false); break;
+      case 7: LSB_HIST(7, false); break;
+      case 8: LSB_HIST(8, false); break;
+      case 9: LSB_HIST(9, false); break;
+      case 10: LSB_HIST(10, false); break;
+      case 11: LSB_HIST(11, false); break;
+      case 12: LSB_HIST(12, false); break;
+      case 13: LSB_HIST(13, false); break;
+      case 14: LSB_HIST(14, false); break;
+      case 15: LSB_HIST(15, false); break;
+      default: LSB_HIST(16, false); break;
+    }
+#undef LSB_HIST
     c->launches++;
   }
   CU(c, cudaGetLastError());
@@ -271,6 +293,8 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
       case 1: partition_kernel<PartCfgB><<<(unsigned)max_tiles, PartCfgB::THREADS, PartCfgB::SMEM, c->stream>>>(a); break;
       case 2: partition_kernel<PartCfgC><<<(unsigned)max_tiles, PartCfgC::THREADS, PartCfgC::SMEM, c->stream>>>(a); break;
       case 3: partition_kernel<PartCfgD><<<(unsigned)max_tiles, PartCfgD::THREADS, PartCfgD::SMEM, c->stream>>>(a); break;
+      case 4: partition_kernel<PartCfgE><<<(unsigned)max_tiles, PartCfgE::THREADS, PartCfgE::SMEM, c->stream>>>(a); break;
+      case 5: partition_kernel<PartCfgF><<<(unsigned)max_tiles, PartCfgF::THREADS, PartCfgF::SMEM, c->stream>>>(a); break;
       default: partition_kernel<PartCfgA><<<(unsigned)max_tiles, PartCfgA::THREADS, PartCfgA::SMEM, c->stream>>>(a); break;
     }
     c->launches++;
@@ -468,9 +492,9 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   c->peer[1][c->my] = c->buf[1];
   {
     const char* v = getenv("LSB_PT_VARIANT");
-    c->variant = v ? atoi(v) : 3;  // PartCfgD measured fastest on B200 (profiles/)
-    if (c->variant < 0 || c->variant > 3) c->variant = 3;
-    const int tiles[4] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE};
+    c->variant = v ? atoi(v) : 4;  // PartCfgE measured fastest on B200 (profiles/)
+    if (c->variant < 0 || c->variant > 5) c->variant = 4;
+    const int tiles[6] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE, PartCfgE::TILE, PartCfgF::TILE};
     c->tile = tiles[c->variant];
   }
   c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
@@ -500,6 +524,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   LSB_SET_ATTR(PartCfgB)
   LSB_SET_ATTR(PartCfgC)
   LSB_SET_ATTR(PartCfgD)
+  LSB_SET_ATTR(PartCfgE)
+  LSB_SET_ATTR(PartCfgF)
 #undef LSB_SET_ATTR
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC

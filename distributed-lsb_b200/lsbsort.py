@@ -16,7 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB_PATH = os.path.join(_HERE, "liblsbsort.so")
+_LIB_PATH = os.environ.get("LSB_LIBRARY", os.path.join(_HERE, "liblsbsort.so"))  # override: kernel experiments
 _HEADER = os.path.join(_ROOT, "include", "lsbsort.h")
 
 ELT = np.dtype([("key", "<u8"), ("val", "<u8")])  # SortElement, mpi/mpi_lsbsort.cpp:29-32
