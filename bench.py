@@ -231,7 +231,13 @@ def main_cuda(args, rank, world, local_rank):
     achieved = here * 32 / (launch_ms * 1e-3) / 1e9
     npass = sorter.num_passes()
     sort_ms = statistics.mean(step_ms)
-    pass_achieved = here * 32 * npass / (sort_ms * 1e-3) / 1e9
+    # t_pass >= max(m*32 B / BW_hbm, m*16 B*f_remote / BW_nvlink); NVLink denominator =
+    # the measured peer-copy figure of B200_PROFILING.md (770 GB/s per direction per GPU, 900 nominal)
+    nvlink_gbs = 770.0
+    f_remote = lsb.hostlogic.remote_fraction(list(st.sent[:world]), rank) if world > 1 else 0.0
+    t_pass_min = lsb.hostlogic.pass_roofline_ms(here, f_remote, peak, nvlink_gbs)
+    pass_bound = "hbm" if here * 32 / (peak * 1e9) >= here * 16 * f_remote / (nvlink_gbs * 1e9) else "nvlink"
+    pass_frac = t_pass_min * npass / sort_ms
     traffic = None
     tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
     if os.path.exists(tp):
@@ -279,11 +285,13 @@ def main_cuda(args, rank, world, local_rank):
                          "launches_per_sort": kp_n,
                          "note": "a launch reads and writes every 16-byte element once (32 B/elem); a 16-bit "
                                  "reference pass takes two launches, see pass_roofline"},
-            "pass_roofline": {"bound": "hbm" if world == 1 else "nvlink",
-                              "algorithmic_bytes_per_sort": here * 32 * npass, "achieved": pass_achieved,
-                              "peak": peak, "unit": "GB/s", "frac": pass_achieved / peak,
-                              "note": "SURVEY 8(d): 32 B per element per reference pass over the whole sort time "
-                                      "(histogram + all partition launches)"},
+            "pass_roofline": {"bound": pass_bound, "t_pass_min_ms": t_pass_min, "t_pass_ms": sort_ms / npass,
+                              "frac": pass_frac, "f_remote": f_remote, "hbm_gbs": peak, "nvlink_gbs": nvlink_gbs,
+                              "algorithmic_bytes_per_pass_hbm": here * 32,
+                              "algorithmic_bytes_per_pass_nvlink": here * 16 * f_remote,
+                              "note": "SURVEY 8(d): slower of 32 B/element of HBM traffic and 16 B x f_remote of "
+                                      "NVLink traffic per reference pass, over the whole sort time (counts, scans, "
+                                      "all partition launches, exchange)"},
             "hist_ms_per_sort": statistics.mean(hist_ms),
         }
         if world == 1 and not args.no_cpu_baseline:

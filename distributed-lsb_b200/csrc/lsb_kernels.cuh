@@ -704,6 +704,54 @@ typedef PartCfg<512, 11, 2> PartCfgE;  // 5632-element tiles, 109 KiB, 32 warps/
 typedef PartCfg<640, 8, 2> PartCfgF;   // 5120-element tiles, 102 KiB, 40 warps/SM
 
 // ------------------------------------------------------------------------------------
+// exchange kernel (G > 1): the pack / MPI_Alltoallv / unpack of mpi/mpi_lsbsort.cpp:530-576
+// as ONE pass over the shard once it is sorted by the full digit.  Element i of digit d goes to
+// global index mybase[d] + (i - localbase[d]) (== `starts[bucket]++`, :550-552) and is stored
+// straight into the owning GPU's shard (16 bytes on the wire, not the reference's 24).  A run
+// (digit, this GPU) is contiguous on both sides, so the NVLink stores are long aligned bursts:
+// measured 716 GB/s per direction for runs >= 128 B, against 220-620 GB/s (shard-size dependent:
+// TLB set conflicts on cross-process peer mappings) when the 22-element runs of the scatter
+// kernel are stored remotely (tools/p2p_bench.cu, tools/p2p_ipc_bench.cu).
+// ------------------------------------------------------------------------------------
+constexpr int EX_THREADS = 512;
+constexpr int EX_U = 4;
+
+struct ExchArgs {
+  const Elt* src;
+  int64_t m;
+  int32_t shift;
+  uint32_t mask;
+  const int64_t* localbase;  // [nb] first local index of digit d in src
+  const int64_t* mybase;     // [nb] global output index of this shard's first element of digit d
+  int64_t per;
+  int32_t world;
+  Elt* dst[8];
+};
+
+__global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) {
+  const int64_t chunk = (int64_t)EX_THREADS * EX_U;
+  for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < a.m; c0 += (int64_t)gridDim.x * chunk) {
+    Elt e[EX_U];
+#pragma unroll
+    for (int u = 0; u < EX_U; u++) {
+      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
+      if (i < a.m) e[u] = ld_stream(a.src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < EX_U; u++) {
+      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
+      if (i < a.m) {
+        const unsigned d = (unsigned)(e[u].key >> a.shift) & a.mask;
+        const long long g = __ldg(a.mybase + d) + (i - __ldg(a.localbase + d));
+        int r = 0;
+        for (int q = 1; q < a.world; q++) r += (g >= (long long)q * a.per);
+        st_elt(a.dst[r] + (g - (long long)r * a.per), e[u]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // verification: strictly increasing (key,val) + multiset hash (mpi/mpi_lsbsort.cpp:710-739)
 // ------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k, uint64_t v) {

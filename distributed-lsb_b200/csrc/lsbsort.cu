@@ -67,6 +67,7 @@ struct lsb_ctx {
   unsigned long long* counts_local = nullptr;  // [65536]
   unsigned long long* counts_all = nullptr;    // [G][65536]
   int64_t* mybase = nullptr;                 // [65536]
+  int64_t* localbase = nullptr;              // [65536]
   uint32_t* seg_tile_start = nullptr;        // [257]
   int64_t* one_seg_start = nullptr;          // {0, here}
   uint32_t* one_seg_tiles = nullptr;         // {0, ceil(here/TILE)}
@@ -189,6 +190,7 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
     switch (c->phase_kind[i]) {
       case 0: st->hist_ms += d; break;
       case 1: st->scan_ms += d; break;
+      case 3: st->exchange_ms += d; break;
       case 2:
         st->partition_ms += d;
         if (sp < LSB_MAX_SUBPASSES) st->subpass_ms[sp] = d;
@@ -374,17 +376,66 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
     CU(c, cudaGetLastError());
   }
   if ((rc = phase_mark(c, 0))) return rc;
-  // the all-gather doubles as the barrier "every GPU is done reading the shard that is
-  // about to be overwritten by its peers"
-  if ((rc = global_offsets(c, nb))) return rc;
+  if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) {
+    // the all-gather doubles as the barrier "every GPU is done reading the shard that is
+    // about to be overwritten by its peers"
+    if ((rc = global_offsets(c, nb))) return rc;
+    if ((rc = phase_mark(c, 1))) return rc;
+    if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
+                               dst_buf, true)))
+      return rc;
+    (*subpasses)++;
+    // peers' stores into my shard must have landed before anything reads it
+    if ((rc = stream_barrier(c))) return rc;
+    c->cur = dst_buf;
+    return LSB_OK;
+  }
+  // local offsets of every digit: exclusive scan of this shard's counts in digit order
+  {
+    GlobalScanArgs s;
+    s.counts = c->counts_local;
+    s.nb = nb;
+    s.G = 1;
+    s.my = 0;
+    s.per = INT64_MAX / 16;
+    s.mybase = c->localbase;
+    s.sent = nullptr;
+    global_scan_kernel<<<1, 1024, 0, c->stream>>>(s);
+    c->launches++;
+    CU(c, cudaGetLastError());
+  }
   if ((rc = phase_mark(c, 1))) return rc;
-  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
-                             dst_buf, true)))
+  // high sub-digit, still local: the shard is now sorted by the full digit (== localShuffle, :213-247)
+  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->localbase,
+                             dst_buf, false)))
     return rc;
   (*subpasses)++;
+  // count all-gather + digit-major/rank-minor scan (:327-479); queued after the local sort it is also
+  // the barrier "every GPU is done reading the buffer its peers are about to overwrite"
+  if ((rc = global_offsets(c, nb))) return rc;
+  if ((rc = phase_mark(c, 1))) return rc;
+  const int xbuf = dst_buf ^ 1;
+  if (c->here > 0) {
+    ExchArgs x;
+    memset(&x, 0, sizeof(x));
+    x.src = c->buf[dst_buf];
+    x.m = c->here;
+    x.shift = p.shift;
+    x.mask = (uint32_t)(nb - 1);
+    x.localbase = c->localbase;
+    x.mybase = c->mybase;
+    x.per = c->per;
+    x.world = c->G;
+    for (int g = 0; g < c->G; g++) x.dst[g] = c->peer[xbuf][g];
+    const int grid = (int)std::min<int64_t>(148 * 8, div_ceil(c->here, (int64_t)EX_THREADS * EX_U));
+    exchange_kernel<<<grid, EX_THREADS, 0, c->stream>>>(x);
+    c->launches++;
+    CU(c, cudaGetLastError());
+  }
+  if ((rc = phase_mark(c, 3))) return rc;
   // peers' stores into my shard must have landed before anything reads it
   if ((rc = stream_barrier(c))) return rc;
-  c->cur = dst_buf;
+  c->cur = xbuf;
   return LSB_OK;
 }
 
@@ -506,6 +557,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->counts_local, sizeof(unsigned long long) * 65536));
   CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
   CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
+  CUC(cudaMalloc(&c->localbase, sizeof(int64_t) * 65536));
   CUC(cudaMalloc(&c->seg_tile_start, sizeof(uint32_t) * 257));
   CUC(cudaMalloc(&c->one_seg_start, sizeof(int64_t) * 2));
   CUC(cudaMalloc(&c->one_seg_tiles, sizeof(uint32_t) * 2));
@@ -551,6 +603,7 @@ void lsb_destroy(lsb_ctx* c) {
   cudaFree(c->counts_local);
   cudaFree(c->counts_all);
   cudaFree(c->mybase);
+  cudaFree(c->localbase);
   cudaFree(c->seg_tile_start);
   cudaFree(c->one_seg_start);
   cudaFree(c->one_seg_tiles);

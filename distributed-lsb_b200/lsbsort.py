@@ -26,6 +26,7 @@ LSB_MAX_SUBPASSES = 32
 LSB_COMM_ID_BYTES = 128
 FLAG_PHASE_EVENTS = 1
 FLAG_TWO_LEVEL = 2
+FLAG_DIRECT_SCATTER = 4
 
 
 class LsbError(RuntimeError):
@@ -44,7 +45,7 @@ class _Config(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("device_ms", ctypes.c_double), ("passes", ctypes.c_int32), ("subpasses", ctypes.c_int32),
                 ("elements", ctypes.c_int64), ("hist_ms", ctypes.c_double), ("scan_ms", ctypes.c_double),
-                ("partition_ms", ctypes.c_double), ("subpass_ms", ctypes.c_double * LSB_MAX_SUBPASSES),
+                ("partition_ms", ctypes.c_double), ("exchange_ms", ctypes.c_double), ("subpass_ms", ctypes.c_double * LSB_MAX_SUBPASSES),
                 ("sent", ctypes.c_int64 * LSB_MAX_GPUS), ("partition_launches", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64)]
 

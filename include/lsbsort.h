@@ -81,6 +81,9 @@ typedef struct lsb_config {
 
 #define LSB_FLAG_NONE 0u
 #define LSB_FLAG_PHASE_EVENTS 1u /* record a CUDA event after every kernel of lsb_sort      */
+#define LSB_FLAG_DIRECT_SCATTER 4u /* G > 1: let the scatter kernel store its 20-element runs
+                                      directly into the peers (no separate exchange kernel); faster
+                                      below ~2^28 elements per GPU, slower above  */
 #define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (segment count + global scan +
                                     segmented scatter) even when world_size == 1            */
 
@@ -92,7 +95,8 @@ typedef struct lsb_stats {
   int64_t elements;       /* elements of THIS shard that took part                         */
   double hist_ms;         /* count kernels (needs LSB_FLAG_PHASE_EVENTS, else 0)           */
   double scan_ms;         /* scans + collectives on counts                                 */
-  double partition_ms;    /* partition (scatter/exchange) kernels                          */
+  double partition_ms;    /* partition (scatter) kernels                                   */
+  double exchange_ms;     /* G > 1: exchange kernels (NVLink stores)                       */
   double subpass_ms[LSB_MAX_SUBPASSES]; /* per partition-kernel launch                     */
   int64_t sent[LSB_MAX_GPUS]; /* last pass: elements this shard sent to each GPU (:553-554) */
   int64_t partition_launches;

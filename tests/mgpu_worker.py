@@ -32,10 +32,13 @@ def main():
         (1, 1, 16, ALL, 1), (65537, 3, 16, ALL, 1), (1 << 20, 4, 8, ALL, 1), (1 << 20, 4, 11, ALL, 1),
         (700001, 4, 16, 0xFFFFFF, 1), (500000, 2, 16, ALL, 3), (300000, 4, 16, 0, 1), (1 << 22, world, 16, ALL, 1),
     ]
-    for n, R, bits, mask, k in cases:
+    from distributed_lsb_b200 import lsbsort as L
+    for ci, (n, R, bits, mask, k) in enumerate(cases):
         g = O.generate(n, R, key_mask=mask, and_draws=k)
         want = O.sort(g, n, R, bits)
-        s = make(n, R, rank, world, radix_bits=bits, key_mask=mask, and_draws=k)
+        # every other case also through the direct-scatter variant of the exchange
+        flags = L.FLAG_DIRECT_SCATTER if ci % 2 else 0
+        s = make(n, R, rank, world, radix_bits=bits, key_mask=mask, and_draws=k, flags=flags)
         lo, hi = s.first_global, s.first_global + s.here
         s.generate()
         assert (s.download() == g[lo:hi]).all(), ("generate", n, R)

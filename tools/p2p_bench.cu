@@ -1,0 +1,88 @@
+// p2p_bench.cu -- how fast can a kernel store 16-byte elements into a peer GPU over NVLink as a
+// function of the contiguous run length?  (design evidence for the exchange step; 2 GPUs, one process)
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o p2p_bench tools/p2p_bench.cu && ./p2p_bench
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+struct __align__(16) Elt { uint64_t k, v; };
+
+// thread i writes element i of the source to dst[perm(run(i)) * R + i % R]: runs of R elements land at
+// pseudo-random run slots; `skew` shifts every run start by that many elements (mis-alignment)
+__global__ void scatter_runs(const Elt* __restrict__ src, Elt* dst, int64_t n, int log2R, int64_t nruns, int skew) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t run = i >> log2R, within = i & ((1 << log2R) - 1);
+    const int64_t slot = (run * 2654435761LL + 12345) & (nruns - 1);  // nruns is a power of two; odd multiplier = permutation
+    Elt e = src[i];
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + (slot << log2R) + within + skew), "l"(e.k), "l"(e.v) : "memory");
+  }
+}
+
+// the sort's pattern: tiles of T elements, each tile appends T/256 elements to each of 256 frontiers
+// that are n/256 apart (destination regions of one segment); `half`: only odd bins go to dst2
+__global__ void scatter_frontier(const Elt* __restrict__ src, Elt* dst, Elt* dst2, int64_t n, int T) {
+  const int run = T / 256;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t region = n / 256;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t tile = i / T;
+    const int p = (int)(i - tile * T);
+    const int bin = p / run, off = p - bin * run;
+    if (bin >= 256) continue;
+    Elt e = src[i];
+    Elt* base = (bin & 1) ? dst2 : dst;
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(base + bin * region + tile * run + off), "l"(e.k), "l"(e.v) : "memory");
+  }
+}
+
+int main(int argc, char** argv) {
+  int nd = 0;
+  CK(cudaGetDeviceCount(&nd));
+  if (nd < 2) { printf("needs 2 GPUs\n"); return 0; }
+  const int64_t n = 1LL << (argc > 1 ? atoi(argv[1]) : 27);
+  Elt *src, *local, *remote;
+  CK(cudaSetDevice(1));
+  CK(cudaMalloc(&remote, (n + 64) * sizeof(Elt)));
+  CK(cudaSetDevice(0));
+  CK(cudaDeviceEnablePeerAccess(1, 0));
+  CK(cudaMalloc(&src, n * sizeof(Elt)));
+  CK(cudaMalloc(&local, (n + 64) * sizeof(Elt)));
+  CK(cudaMemset(src, 1, n * sizeof(Elt)));
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a));
+  CK(cudaEventCreate(&b));
+  {
+    float ms = 0;
+    for (int T = 2048; T <= 8192; T += 3584) {
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(a));
+        scatter_frontier<<<148 * 8, 512>>>(src, local, remote, n, T);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&ms, a, b));
+      }
+      printf("frontier pattern T=%d (run %d el), half of the bins to the peer: %.2f ms, %.0f GB/s to peer, %.0f GB/s total\n", T, T / 256,
+             ms, n * 8.0 / ms / 1e6, n * 16.0 / ms / 1e6);
+    }
+  }
+  printf("%-8s %-6s %12s %12s\n", "run(el)", "skew", "local GB/s", "peer GB/s");
+  for (int skew = 0; skew <= 3; skew += 3)
+    for (int lr = (argc > 2 ? 3 : 0); lr <= (argc > 2 ? 5 : 14); lr += (lr < 8 ? 1 : 3)) {
+      float ms[2];
+      for (int t = 0; t < 2; t++) {
+        Elt* dst = t ? remote : local;
+        for (int rep = 0; rep < 3; rep++) {
+          CK(cudaEventRecord(a));
+          scatter_runs<<<148 * 8, 512>>>(src, dst, n, lr, n >> lr, skew);
+          CK(cudaEventRecord(b));
+          CK(cudaEventSynchronize(b));
+          CK(cudaEventElapsedTime(&ms[t], a, b));
+        }
+      }
+      printf("%-8d %-6d %12.0f %12.0f\n", 1 << lr, skew, n * 16.0 / ms[0] / 1e6, n * 16.0 / ms[1] / 1e6);
+    }
+  return 0;
+}
