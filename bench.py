@@ -242,7 +242,7 @@ def main_cuda(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            traffic = json.load(f).get("dram_bytes_per_element", 0) * here or None  # per launch of `here` elements
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     e2e = None

@@ -447,6 +447,11 @@ struct PartArgs {
   int64_t per;                     // destination shard size (global index / per = shard)
   int32_t world;
   Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
+  // RUNS kernels only: the input is already grouped by the low bits of a wider digit, so the
+  // sorted tile is ordered by that full digit; count its runs into run_counts[digit]
+  unsigned long long* run_counts;
+  int32_t full_shift;
+  uint32_t full_mask;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -511,7 +516,7 @@ __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
   return peers;
 }
 
-template <class C, bool FULL>
+template <class C, bool FULL, bool RUNS>
 __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
                                                unsigned* s_wtot, int tile, int seg, int count, bool first,
                                                int first_tile) {
@@ -628,8 +633,12 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
 #pragma unroll
   for (int k = 0; k < C::IPT; k++) {
     const int p = k * C::THREADS + tid;
-    if (FULL || p < count) {
-      const Elt el = s_raw[s_perm[p]];
+    const bool valid = FULL || p < count;
+    Elt el;
+    el.key = 0;
+    el.val = 0;
+    if (valid) {
+      el = s_raw[s_perm[p]];
       const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
       const long long g = s_bindst[bin] + p;
       Elt* out;
@@ -642,10 +651,24 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       }
       st_elt(out, el);
     }
+    if (RUNS) {
+      // localShuffle's counts of the FULL digit (:226-229) as a by-product: the sorted tile is
+      // non-decreasing in the full digit, so each warp adds the length of every run it sees
+      const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
+      const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
+      const bool head = valid && (lane == 0 || d != prev);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const unsigned nvalid = FULL ? 32u : (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
+      if (head) {
+        const unsigned after = heads & ~((2u << lane) - 1u);
+        const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
+        atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
+      }
+    }
   }
 }
 
-template <class C>
+template <class C, bool RUNS>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_bar;
@@ -690,9 +713,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
   __syncthreads();
   const int count = s_count;
   if (count == C::TILE)
-    partition_tile<C, true>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+    partition_tile<C, true, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
   else
-    partition_tile<C, false>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+    partition_tile<C, false, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
 }
 
 // tile shapes: {threads, elements per thread, CTAs per SM}; all need nseg <= THREADS

@@ -260,7 +260,8 @@ int launch_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
 }
 
 int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bits, const int64_t* seg_start,
-                     const uint32_t* seg_tile_start, const int64_t* bases, int dst_buf, bool global_dst) {
+                     const uint32_t* seg_tile_start, const int64_t* bases, int dst_buf, bool global_dst,
+                     int full_shift = -1, int full_bits = 0) {
   if (c->gen > 126) {  // tags exhausted: wipe the look-back words and start over
     CU(c, cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
     c->gen = 0;
@@ -291,14 +292,24 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
   }
   const int64_t max_tiles = div_ceil(c->here, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
   if (c->here > 0) {
-    switch (c->variant) {
-      case 1: partition_kernel<PartCfgB><<<(unsigned)max_tiles, PartCfgB::THREADS, PartCfgB::SMEM, c->stream>>>(a); break;
-      case 2: partition_kernel<PartCfgC><<<(unsigned)max_tiles, PartCfgC::THREADS, PartCfgC::SMEM, c->stream>>>(a); break;
-      case 3: partition_kernel<PartCfgD><<<(unsigned)max_tiles, PartCfgD::THREADS, PartCfgD::SMEM, c->stream>>>(a); break;
-      case 4: partition_kernel<PartCfgE><<<(unsigned)max_tiles, PartCfgE::THREADS, PartCfgE::SMEM, c->stream>>>(a); break;
-      case 5: partition_kernel<PartCfgF><<<(unsigned)max_tiles, PartCfgF::THREADS, PartCfgF::SMEM, c->stream>>>(a); break;
-      default: partition_kernel<PartCfgA><<<(unsigned)max_tiles, PartCfgA::THREADS, PartCfgA::SMEM, c->stream>>>(a); break;
+    const bool runs = full_shift >= 0;
+    if (runs) {
+      a.run_counts = c->counts_local;
+      a.full_shift = full_shift;
+      a.full_mask = (1u << full_bits) - 1;
     }
+#define LSB_PART(CFG)                                                                                         \
+    if (runs) partition_kernel<CFG, true><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a);     \
+    else partition_kernel<CFG, false><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a)
+    switch (c->variant) {
+      case 0: LSB_PART(PartCfgA); break;
+      case 1: LSB_PART(PartCfgB); break;
+      case 2: LSB_PART(PartCfgC); break;
+      case 3: LSB_PART(PartCfgD); break;
+      case 5: LSB_PART(PartCfgF); break;
+      default: LSB_PART(PartCfgE); break;
+    }
+#undef LSB_PART
     c->launches++;
   }
   CU(c, cudaGetLastError());
@@ -334,8 +345,9 @@ int global_offsets(lsb_ctx* c, int nb) {
   return LSB_OK;
 }
 
-// one reference pass, multi-GPU shape (also correct for G == 1)
-int pass_global(lsb_ctx* c, int digit, int* subpasses) {
+// one reference pass, multi-GPU shape (also correct for G == 1), exchange by direct scatter:
+// the high sub-digit step stores its runs straight into the peers (LSB_FLAG_DIRECT_SCATTER)
+int pass_global_direct(lsb_ctx* c, int digit, int* subpasses) {
   const PassPlan p = plan_pass(c, digit);
   const int other = c->cur ^ 1;
   const Elt* src2 = c->buf[c->cur];
@@ -376,19 +388,45 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
     CU(c, cudaGetLastError());
   }
   if ((rc = phase_mark(c, 0))) return rc;
-  if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) {
-    // the all-gather doubles as the barrier "every GPU is done reading the shard that is
-    // about to be overwritten by its peers"
-    if ((rc = global_offsets(c, nb))) return rc;
-    if ((rc = phase_mark(c, 1))) return rc;
-    if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
-                               dst_buf, true)))
+  // the all-gather doubles as the barrier "every GPU is done reading the shard that is
+  // about to be overwritten by its peers"
+  if ((rc = global_offsets(c, nb))) return rc;
+  if ((rc = phase_mark(c, 1))) return rc;
+  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
+                             dst_buf, true)))
+    return rc;
+  (*subpasses)++;
+  // peers' stores into my shard must have landed before anything reads it
+  if ((rc = stream_barrier(c))) return rc;
+  c->cur = dst_buf;
+  return LSB_OK;
+}
+
+// one reference pass, multi-GPU shape (also correct for G == 1):
+//   1. ONE read counts both sub-digits of the shard (256 bins each);
+//   2. local stable step on the low bits, local stable step on the high bits: the shard is sorted
+//      by the full digit (== localShuffle, :213-247); the second step also emits the shard's
+//      counts of the full digit from the runs it writes (== counts, :226-229);
+//   3. count all-gather + digit-major/rank-minor scan (== :327-479);
+//   4. exchange kernel: every run goes to its global position in the owning GPU's shard (== :530-576).
+int pass_global(lsb_ctx* c, int digit, int* subpasses) {
+  if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) return pass_global_direct(c, digit, subpasses);
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits;
+  int rc;
+  SubPass subs[2];
+  int ns = 0;
+  if (p.lo_bits) subs[ns++] = {p.shift, p.lo_bits};
+  subs[ns++] = {p.shift + p.lo_bits, p.hi_bits};
+  if ((rc = launch_hist(c, c->buf[c->cur], subs, ns))) return rc;
+  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
+  for (int s = 0; s < ns; s++) {
+    const bool last = (s == ns - 1);
+    if ((rc = launch_partition(c, c->buf[c->cur], subs[s].shift, subs[s].bits, 0, c->one_seg_start, c->one_seg_tiles,
+                               c->scan_out + (size_t)s * 257, c->cur ^ 1, false, last ? p.shift : -1, p.bits)))
       return rc;
+    c->cur ^= 1;
     (*subpasses)++;
-    // peers' stores into my shard must have landed before anything reads it
-    if ((rc = stream_barrier(c))) return rc;
-    c->cur = dst_buf;
-    return LSB_OK;
   }
   // local offsets of every digit: exclusive scan of this shard's counts in digit order
   {
@@ -404,21 +442,15 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
     c->launches++;
     CU(c, cudaGetLastError());
   }
-  if ((rc = phase_mark(c, 1))) return rc;
-  // high sub-digit, still local: the shard is now sorted by the full digit (== localShuffle, :213-247)
-  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->localbase,
-                             dst_buf, false)))
-    return rc;
-  (*subpasses)++;
-  // count all-gather + digit-major/rank-minor scan (:327-479); queued after the local sort it is also
-  // the barrier "every GPU is done reading the buffer its peers are about to overwrite"
+  // queued after the local sort, the all-gather is also the barrier "every GPU is done reading the
+  // buffer its peers are about to overwrite"
   if ((rc = global_offsets(c, nb))) return rc;
   if ((rc = phase_mark(c, 1))) return rc;
-  const int xbuf = dst_buf ^ 1;
+  const int xbuf = c->cur ^ 1;
   if (c->here > 0) {
     ExchArgs x;
     memset(&x, 0, sizeof(x));
-    x.src = c->buf[dst_buf];
+    x.src = c->buf[c->cur];
     x.m = c->here;
     x.shift = p.shift;
     x.mask = (uint32_t)(nb - 1);
@@ -570,8 +602,10 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
   CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
 #define LSB_SET_ATTR(CFG)                                                                                   \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM)); \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM)); \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));  \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   LSB_SET_ATTR(PartCfgA)
   LSB_SET_ATTR(PartCfgB)
   LSB_SET_ATTR(PartCfgC)
