@@ -752,8 +752,26 @@ struct ExchArgs {
 };
 
 __global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) {
+  // The shard is sorted by digit, so positions [k*m/G, (k+1)*m/G) go (roughly) to GPU k.  Chunks are
+  // dealt round-robin over those G parts so that at any moment the resident CTAs store to all G
+  // destinations at once: the local part (HBM-bound) overlaps the remote parts (NVLink-bound).
+  __shared__ Elt* s_dst[8];  // (indexing the kernel parameter dynamically would spill it to local memory)
+  __shared__ long long s_lim[8];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      s_dst[q] = a.dst[q];
+      s_lim[q] = (long long)q * a.per;
+    }
+  }
+  __syncthreads();
   const int64_t chunk = (int64_t)EX_THREADS * EX_U;
-  for (int64_t c0 = (int64_t)blockIdx.x * chunk; c0 < a.m; c0 += (int64_t)gridDim.x * chunk) {
+  const int64_t part = ((a.m + a.world - 1) / a.world + chunk - 1) / chunk * chunk;  // multiple of chunk
+  const int64_t chunks_per_part = part / chunk;
+  const int64_t total = chunks_per_part * a.world;
+  for (int64_t k = blockIdx.x; k < total; k += gridDim.x) {
+    const int64_t c0 = (k % a.world) * part + (k / a.world) * chunk;
+    if (c0 >= a.m) continue;
     Elt e[EX_U];
 #pragma unroll
     for (int u = 0; u < EX_U; u++) {
@@ -767,8 +785,8 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) 
         const unsigned d = (unsigned)(e[u].key >> a.shift) & a.mask;
         const long long g = __ldg(a.mybase + d) + (i - __ldg(a.localbase + d));
         int r = 0;
-        for (int q = 1; q < a.world; q++) r += (g >= (long long)q * a.per);
-        st_elt(a.dst[r] + (g - (long long)r * a.per), e[u]);
+        for (int q = 1; q < a.world; q++) r += (g >= s_lim[q]);
+        st_elt(s_dst[r] + (g - s_lim[r]), e[u]);
       }
     }
   }
