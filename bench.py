@@ -101,8 +101,8 @@ def cpu_baseline(sample_log2=None):
     ranks = max(1, min(cores, 64))
     n = 1 << (sample_log2 or 24)
     rate, secs = run_reference_once(n, ranks)
-    if sample_log2 is None and secs < 1.5:  # fast host: take a bigger, steadier sample
-        n = 1 << 26
+    if sample_log2 is None and secs < 1.5:  # fast host: take a bigger, steadier sample (~10-20 s of CPU work)
+        n = 1 << 28
         rate, secs = run_reference_once(n, ranks)
     return {"value": rate, "unit": UNIT, "cores": ranks, "kind": "reference",
             "sample": f"unmodified mpi/mpi_lsbsort.cpp over the ranks-as-threads mpi.h shim (oracle/_ref), "

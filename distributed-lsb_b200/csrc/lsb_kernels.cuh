@@ -720,11 +720,11 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
 
 // tile shapes: {threads, elements per thread, CTAs per SM}; all need nseg <= THREADS
 typedef PartCfg<256, 8, 5> PartCfgA;   // 2048-element tiles, 43 KiB, 40 warps/SM
-typedef PartCfg<512, 8, 2> PartCfgB;   // 4096-element tiles, 82 KiB, 32 warps/SM
-typedef PartCfg<384, 8, 3> PartCfgC;   // 3072-element tiles, 62 KiB, 36 warps/SM
+typedef PartCfg<256, 14, 3> PartCfgB;  // 3584-element tiles, 69 KiB, 24 warps/SM
+typedef PartCfg<256, 10, 4> PartCfgC;  // 2560-element tiles, 51 KiB, 32 warps/SM
 typedef PartCfg<512, 10, 2> PartCfgD;  // 5120-element tiles, 100 KiB, 32 warps/SM
 typedef PartCfg<512, 11, 2> PartCfgE;  // 5632-element tiles, 109 KiB, 32 warps/SM
-typedef PartCfg<640, 8, 2> PartCfgF;   // 5120-element tiles, 102 KiB, 40 warps/SM
+typedef PartCfg<256, 22, 2> PartCfgF;  // 5632-element tiles, 105 KiB, 16 warps/SM
 
 // ------------------------------------------------------------------------------------
 // exchange kernel (G > 1): the pack / MPI_Alltoallv / unpack of mpi/mpi_lsbsort.cpp:530-576
@@ -751,7 +751,7 @@ struct ExchArgs {
   Elt* dst[8];
 };
 
-__global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) {
+__global__ void __launch_bounds__(EX_THREADS, 4) exchange_kernel(const ExchArgs a) {
   // The shard is sorted by digit, so positions [k*m/G, (k+1)*m/G) go (roughly) to GPU k.  Chunks are
   // dealt round-robin over those G parts so that at any moment the resident CTAs store to all G
   // destinations at once: the local part (HBM-bound) overlaps the remote parts (NVLink-bound).

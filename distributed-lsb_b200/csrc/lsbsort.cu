@@ -80,6 +80,8 @@ struct lsb_ctx {
   std::vector<cudaEvent_t> phase_ev;
   std::vector<int> phase_kind;  // 0 hist, 1 scan/collective, 2 partition
   int64_t launches = 0;
+  int skipped = 0;
+  unsigned long long* host_hist = nullptr;  // pinned [HIST_MAX_SUB][256]
   std::string err;
 };
 
@@ -164,6 +166,7 @@ int begin_call(lsb_ctx* c) {
   c->phase_ev.clear();
   c->phase_kind.clear();
   c->launches = 0;
+  c->skipped = 0;
   c->next_counter = 0;
   CU(c, cudaMemsetAsync(c->tile_counters, 0, 64 * sizeof(uint32_t), c->stream));
   CU(c, cudaEventRecord(c->ev_start, c->stream));
@@ -181,6 +184,7 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
   st->device_ms = ms;
   st->passes = passes;
   st->subpasses = subpasses;
+  st->skipped = c->skipped;
   st->elements = c->here;
   st->kernel_launches = c->launches;
   int sp = 0;
@@ -483,8 +487,18 @@ int passes_single(lsb_ctx* c, int d0, int d1, int* subpasses) {
   for (size_t s0 = 0; s0 < subs.size(); s0 += HIST_MAX_SUB) {
     const int ns = (int)std::min<size_t>(HIST_MAX_SUB, subs.size() - s0);
     if ((rc = launch_hist(c, c->buf[c->cur], subs.data() + s0, ns))) return rc;
+    const bool may_skip = !(c->cfg.flags & LSB_FLAG_NO_SKIP) && c->here > 0;
+    if (may_skip) {  // a digit that is constant over the shard makes its stable pass the identity
+      CU(c, cudaMemcpyAsync(c->host_hist, c->hist, sizeof(unsigned long long) * 256 * ns, cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+    }
     for (int s = 0; s < ns; s++) {
       const SubPass& sp = subs[s0 + s];
+      if (may_skip) {
+        bool constant = false;
+        for (int b = 0; b < 256; b++) constant = constant || c->host_hist[s * 256 + b] == (unsigned long long)c->here;
+        if (constant) { c->skipped++; continue; }
+      }
       if ((rc = launch_partition(c, c->buf[c->cur], sp.shift, sp.bits, 0, c->one_seg_start, c->one_seg_tiles,
                                  c->scan_out + (size_t)s * 257, c->cur ^ 1, false)))
         return rc;
@@ -596,6 +610,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->small, sizeof(unsigned long long) * 64));
   CUC(cudaMalloc(&c->small_all, sizeof(unsigned long long) * 16 * LSB_MAX_GPUS));
   CUC(cudaMemsetAsync(c->small, 0, sizeof(unsigned long long) * 64, c->stream));
+  CUC(cudaHostAlloc(&c->host_hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, cudaHostAllocDefault));
   CUC(cudaHostAlloc(&c->host_small, sizeof(unsigned long long) * (16 * LSB_MAX_GPUS + 64), cudaHostAllocDefault));
   const int64_t seg[2] = {0, c->here};
   const uint32_t tl[2] = {0, (uint32_t)div_ceil(c->here, c->tile)};
@@ -644,6 +659,7 @@ void lsb_destroy(lsb_ctx* c) {
   cudaFree(c->small);
   cudaFree(c->small_all);
   if (c->host_small) cudaFreeHost(c->host_small);
+  if (c->host_hist) cudaFreeHost(c->host_hist);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->stream) cudaStreamDestroy(c->stream);

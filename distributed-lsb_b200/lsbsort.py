@@ -27,6 +27,7 @@ LSB_COMM_ID_BYTES = 128
 FLAG_PHASE_EVENTS = 1
 FLAG_TWO_LEVEL = 2
 FLAG_DIRECT_SCATTER = 4
+FLAG_NO_SKIP = 8
 
 
 class LsbError(RuntimeError):
@@ -43,7 +44,7 @@ class _Config(ctypes.Structure):
 
 
 class Stats(ctypes.Structure):
-    _fields_ = [("device_ms", ctypes.c_double), ("passes", ctypes.c_int32), ("subpasses", ctypes.c_int32),
+    _fields_ = [("device_ms", ctypes.c_double), ("passes", ctypes.c_int32), ("subpasses", ctypes.c_int32), ("skipped", ctypes.c_int32), ("reserved0", ctypes.c_int32),
                 ("elements", ctypes.c_int64), ("hist_ms", ctypes.c_double), ("scan_ms", ctypes.c_double),
                 ("partition_ms", ctypes.c_double), ("exchange_ms", ctypes.c_double), ("subpass_ms", ctypes.c_double * LSB_MAX_SUBPASSES),
                 ("sent", ctypes.c_int64 * LSB_MAX_GPUS), ("partition_launches", ctypes.c_int64),

@@ -84,6 +84,10 @@ typedef struct lsb_config {
 #define LSB_FLAG_DIRECT_SCATTER 4u /* G > 1: let the scatter kernel store its 20-element runs
                                       directly into the peers (no separate exchange kernel); faster
                                       below ~2^28 elements per GPU, slower above  */
+#define LSB_FLAG_NO_SKIP 8u       /* do not skip sub-passes whose digit is constant over the shard
+                                    (a stable pass on a constant digit is the identity; the
+                                    reference always runs it; chpl passes nBits for the same
+                                    purpose, chpl/arkouda-radix-sort.chpl:70,78)              */
 #define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (segment count + global scan +
                                     segmented scatter) even when world_size == 1            */
 
@@ -92,6 +96,8 @@ typedef struct lsb_stats {
   double device_ms;       /* whole call: first kernel start -> last kernel end             */
   int32_t passes;         /* reference passes run (N_DIGITS, :22)                          */
   int32_t subpasses;      /* partition-kernel launches (2 per 16-bit pass)                 */
+  int32_t skipped;        /* sub-passes skipped because their digit was constant           */
+  int32_t reserved0;
   int64_t elements;       /* elements of THIS shard that took part                         */
   double hist_ms;         /* count kernels (needs LSB_FLAG_PHASE_EVENTS, else 0)           */
   double scan_ms;         /* scans + collectives on counts                                 */

@@ -117,6 +117,24 @@ def test_skewed_keys_stable(mask, k, flags):
     assert list(v.checksum) == before and v.order_violations == 0 and v.elements == n
 
 
+def test_constant_digits_are_skipped_not_missorted():
+    # 24-bit keys: sub-digits 3..7 are constant -> 5 of the 8 launches are skipped, same bytes out
+    n, R = 300000, 2
+    g = O.generate(n, R, key_mask=0xFFFFFF)
+    want = O.sort(g, n, R)
+    for flags, skipped in ((0, 5), (L.FLAG_NO_SKIP, 0)):
+        with lsb.DistributedSorter(n, ranks=R, key_mask=0xFFFFFF, flags=flags) as s:
+            s.generate()
+            st = s.my_sort()
+            assert st.skipped == skipped and st.subpasses == 8 - skipped and st.passes == 4
+            assert (s.download() == want).all()
+    with lsb.DistributedSorter(1000, key_mask=0) as s:  # every digit constant: nothing to do at all
+        s.generate()
+        st = s.my_sort()
+        assert st.subpasses == 0 and st.skipped == 8
+        assert (s.download() == O.generate(1000, 1, key_mask=0)[:1000]).all()
+
+
 def test_uploaded_data_and_host_path():
     # caller-supplied records (the reference only sorts generated data): duplicates + arbitrary vals
     rng = np.random.default_rng(5)
