@@ -720,11 +720,261 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
 
 // tile shapes: {threads, elements per thread, CTAs per SM}; all need nseg <= THREADS
 typedef PartCfg<256, 8, 5> PartCfgA;   // 2048-element tiles, 43 KiB, 40 warps/SM
-typedef PartCfg<256, 14, 3> PartCfgB;  // 3584-element tiles, 69 KiB, 24 warps/SM
-typedef PartCfg<256, 10, 4> PartCfgC;  // 2560-element tiles, 51 KiB, 32 warps/SM
+typedef PartCfg<256, 15, 3> PartCfgB;  // 3840-element tiles, 74 KiB, 24 warps/SM
+typedef PartCfg<256, 11, 4> PartCfgC;  // 2816-element tiles, 56 KiB, 32 warps/SM
 typedef PartCfg<512, 10, 2> PartCfgD;  // 5120-element tiles, 100 KiB, 32 warps/SM
 typedef PartCfg<512, 11, 2> PartCfgE;  // 5632-element tiles, 109 KiB, 32 warps/SM
 typedef PartCfg<256, 22, 2> PartCfgF;  // 5632-element tiles, 105 KiB, 16 warps/SM
+
+// ------------------------------------------------------------------------------------
+// persistent partition kernel (single-segment inputs: every step except the direct-scatter
+// variant).  Same algorithm as partition_kernel, different execution shape:
+//   * one CTA of 1024 threads per SM loops over tiles (dynamic tile ids); the NEXT tile is
+//     pulled into the other half of a double-buffered shared-memory stage by a bulk async
+//     copy while the current one is being processed, so the HBM->SMEM latency is hidden;
+//   * 24 worker warps count / rank / write; 8 specialist warps (one thread per bin) own the
+//     per-bin bookkeeping: column sums, publishing the tile aggregate, and the decoupled
+//     look-back -- which now runs CONCURRENTLY with the workers' ranking instead of after it.
+// ------------------------------------------------------------------------------------
+template <int IPT_>
+struct PersistCfg {
+  static constexpr int THREADS = 1024;
+  static constexpr int WORK_WARPS = 24;
+  static constexpr int WORK_THREADS = WORK_WARPS * 32;  // 768; specialists are threads 768..1023
+  static constexpr int IPT = IPT_;                      // rows of 32 elements per worker warp
+  static constexpr int TILE = WORK_WARPS * 32 * IPT_;
+  static constexpr int SLOTS = (TILE + THREADS - 1) / THREADS;
+  static constexpr int SMEM_RAW0 = 0;
+  static constexpr int SMEM_RAW1 = TILE * 16;
+  static constexpr int SMEM_PERM = 2 * TILE * 16;
+  static constexpr int SMEM_WHIST = SMEM_PERM + ((TILE * 2 + 15) / 16) * 16;
+  static constexpr int SMEM_BINDST = SMEM_WHIST + WORK_WARPS * 256 * 2;
+  static constexpr int SMEM = SMEM_BINDST + 256 * 8;
+};
+
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+struct TileDesc {
+  int tile;   // -1: no more work
+  int count;
+};
+
+#ifndef PS_LB_WINDOW
+#define PS_LB_WINDOW 4
+#endif
+template <class C, bool RUNS>
+__global__ void __launch_bounds__(C::THREADS, 1) partition_persistent_kernel(const PartArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
+  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
+  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ TileDesc s_desc[2];
+  __shared__ unsigned s_wtot[8];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool worker = tid < C::WORK_THREADS;
+  const int64_t m = a.seg_start[1];                 // single segment: [0, m)
+  const unsigned total_tiles = a.seg_tile_start[1];
+
+  // start the bulk load of tile `t` into stage `b` (one thread)
+  auto prefetch = [&](int b, unsigned t) {
+    if (t < total_tiles) {
+      const long long begin = (long long)t * C::TILE;
+      const long long left = m - begin;
+      const int cnt = (int)(left < C::TILE ? left : C::TILE);
+      s_desc[b].tile = (int)t;
+      s_desc[b].count = cnt;
+      mbar_expect_tx(&s_bar[b], (unsigned)cnt * 16u);
+      bulk_load(smem + (b ? C::SMEM_RAW1 : C::SMEM_RAW0), a.src + begin, (unsigned)cnt * 16u, &s_bar[b]);
+    } else {
+      s_desc[b].tile = -1;
+      s_desc[b].count = 0;
+    }
+  };
+
+  // tile ids come from an atomic counter; the scheduler thread keeps one id in flight so that the
+  // atomic's round trip never sits in front of a barrier
+  unsigned next_id = 0;
+  if (tid == C::THREADS - 1) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    prefetch(0, atomicAdd(a.tile_counter, 1u));
+    next_id = atomicAdd(a.tile_counter, 1u);
+  }
+  __syncthreads();
+
+  for (int it = 0;; it++) {
+    const int b = it & 1;
+    const int tile = s_desc[b].tile;
+    if (tile < 0) break;
+    const int count = s_desc[b].count;
+    const bool full = (count == C::TILE);
+    const bool first = (tile == 0);
+    Elt* s_raw = reinterpret_cast<Elt*>(smem + (b ? C::SMEM_RAW1 : C::SMEM_RAW0));
+    if (tid == C::THREADS - 1) {  // stage b^1 was released by the barrier that ended the last iteration
+      prefetch(b ^ 1, next_id);
+      if (next_id < total_tiles) next_id = atomicAdd(a.tile_counter, 1u);
+    }
+
+    // ---- workers: early per-warp counts ----
+    const int idx0 = warp * (32 * C::IPT) + lane;
+    unsigned bins[C::IPT];
+    if (worker) {
+      reinterpret_cast<uint4*>(s_whist + warp * 256)[lane] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      while (!mbar_try(&s_bar[b], (unsigned)(it >> 1) & 1u)) {}
+      unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
+#pragma unroll
+      for (int j = 0; j < C::IPT; j++) {
+        const int idx = idx0 + j * 32;
+        bins[j] = 0;
+        if (full || idx < count) {
+          const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
+          bins[j] = bin;
+          atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
+        }
+      }
+    }
+    __syncthreads();  // A
+
+    // ---- specialists: per-bin totals, publish, bin starts, warp offsets ----
+    unsigned tile_count = 0, binstart = 0;
+    uint64_t* my_state = nullptr;
+    const int bin_t = tid - C::WORK_THREADS;  // 0..255 for specialists
+    if (!worker) {
+      my_state = a.lookback + (size_t)tile * 256 + bin_t;
+      unsigned wc[C::WORK_WARPS];
+#pragma unroll
+      for (int w = 0; w < C::WORK_WARPS; w++) {
+        wc[w] = s_whist[w * 256 + bin_t];
+        tile_count += wc[w];
+      }
+      st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
+      unsigned incl = tile_count;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      const int sw = bin_t >> 5;
+      if (lane == 31) s_wtot[sw] = incl;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 specialist warps only
+      binstart = incl - tile_count;
+      for (int i = 0; i < sw; i++) binstart += s_wtot[i];
+      unsigned run = binstart;
+#pragma unroll
+      for (int w = 0; w < C::WORK_WARPS; w++) {
+        s_whist[w * 256 + bin_t] = (unsigned short)run;
+        run += wc[w];
+      }
+    }
+    __syncthreads();  // B
+
+    if (worker) {
+      // ---- stable ranks -> permutation ----
+      unsigned short* wh = s_whist + warp * 256;
+      const unsigned lt = lanemask_lt();
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < C::IPT; j++) {
+          const unsigned bin = bins[j];
+          const unsigned peers = match_bin<true>(0xffffffffu, bin);
+          const unsigned old = wh[bin];
+          __syncwarp();
+          if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+          __syncwarp();
+          s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + j * 32);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < C::IPT; j++) {
+          const int idx = idx0 + j * 32;
+          const bool valid = idx < count;
+          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+          if (valid) {
+            const unsigned bin = bins[j];
+            const unsigned peers = match_bin<false>(vmask, bin);
+            const unsigned old = wh[bin];
+            __syncwarp(vmask);
+            if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+            __syncwarp(vmask);
+            s_perm[old + __popc(peers & lt)] = (unsigned short)idx;
+          }
+        }
+      }
+    } else {
+      // ---- decoupled look-back, concurrent with the ranking ----
+      uint64_t excl = 0;
+      if (!first) {
+        int look = tile - 1;
+        bool done = false;
+        while (!done) {
+          uint64_t v[PS_LB_WINDOW];
+#pragma unroll
+          for (int i = 0; i < PS_LB_WINDOW; i++) {
+            const int t = look - i;
+            v[i] = (t >= 0) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + bin_t) : 0;
+          }
+          int used = 0;
+#pragma unroll
+          for (int i = 0; i < PS_LB_WINDOW; i++) {
+            if (!done && used == i) {
+              const uint64_t tag = v[i] & ~LB_VALUE_MASK;
+              if (tag == a.tag_inc) { excl += v[i] & LB_VALUE_MASK; done = true; }
+              else if (tag == a.tag_agg) { excl += v[i] & LB_VALUE_MASK; used = i + 1; }
+            }
+          }
+          look -= used;
+          if (!done && used == 0) __nanosleep(20);
+        }
+        st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
+      }
+      s_bindst[bin_t] = a.bases[bin_t] + (long long)excl - (long long)binstart;
+    }
+    __syncthreads();  // C
+
+    // ---- write: consecutive threads -> consecutive slots of a bin's run ----
+#pragma unroll
+    for (int k = 0; k < C::SLOTS; k++) {
+      const int p = k * C::THREADS + tid;
+      const bool valid = p < count;
+      Elt el;
+      el.key = 0;
+      el.val = 0;
+      if (valid) {
+        el = s_raw[s_perm[p]];
+        const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
+        st_elt(a.dst[0] + (s_bindst[bin] + p), el);
+      }
+      if (RUNS) {
+        const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
+        const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
+        const bool head = valid && (lane == 0 || d != prev);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
+        if (head) {
+          const unsigned after = heads & ~((2u << lane) - 1u);
+          const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
+          atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
+        }
+      }
+    }
+    __syncthreads();  // D: stage b and perm are free again
+  }
+}
+
+typedef PersistCfg<7> PersistCfgA;  // 5376-element tiles, 2 x 84 KiB stages, 195 KiB
 
 // ------------------------------------------------------------------------------------
 // exchange kernel (G > 1): the pack / MPI_Alltoallv / unpack of mpi/mpi_lsbsort.cpp:530-576
@@ -749,9 +999,18 @@ struct ExchArgs {
   int64_t per;
   int32_t world;
   Elt* dst[8];
+  // optional: while the elements stream by, count the sub-digits of the NEXT pass per destination
+  // GPU (the receiver sums the G contributions), so the next pass needs no count read of its own
+  int32_t next_nsub;              // 0 = off
+  int32_t next_shift[2];
+  uint32_t next_mask[2];
+  unsigned long long* next_hist;  // [G][2][256], caller zeroes
 };
 
-__global__ void __launch_bounds__(EX_THREADS, 4) exchange_kernel(const ExchArgs a) {
+__global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) {
+  __shared__ unsigned s_next[8 * 2 * 256];
+  if (a.next_nsub)
+    for (int i = threadIdx.x; i < a.world * 2 * 256; i += EX_THREADS) s_next[i] = 0;
   // The shard is sorted by digit, so positions [k*m/G, (k+1)*m/G) go (roughly) to GPU k.  Chunks are
   // dealt round-robin over those G parts so that at any moment the resident CTAs store to all G
   // destinations at once: the local part (HBM-bound) overlaps the remote parts (NVLink-bound).
@@ -787,9 +1046,25 @@ __global__ void __launch_bounds__(EX_THREADS, 4) exchange_kernel(const ExchArgs 
         int r = 0;
         for (int q = 1; q < a.world; q++) r += (g >= s_lim[q]);
         st_elt(s_dst[r] + (g - s_lim[r]), e[u]);
+        for (int s = 0; s < a.next_nsub; s++)
+          atomicAdd(&s_next[(r * 2 + s) * 256 + ((unsigned)(e[u].key >> a.next_shift[s]) & a.next_mask[s])], 1u);
       }
     }
   }
+  if (a.next_nsub) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.world * 2 * 256; i += EX_THREADS)
+      if (s_next[i]) atomicAdd(a.next_hist + i, (unsigned long long)s_next[i]);
+  }
+}
+
+// hist[s][bin] = sum over source GPUs of next_hist_all[src][my][s][bin]  (blockDim = 512, one block)
+__global__ void __launch_bounds__(512) next_hist_reduce_kernel(const unsigned long long* all, int G, int my,
+                                                              unsigned long long* hist) {
+  const int i = threadIdx.x;  // (s, bin)
+  unsigned long long acc = 0;
+  for (int src = 0; src < G; src++) acc += all[((size_t)src * G + my) * 512 + i];
+  hist[i] = acc;
 }
 
 // ------------------------------------------------------------------------------------

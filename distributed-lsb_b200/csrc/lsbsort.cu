@@ -60,7 +60,8 @@ struct lsb_ctx {
   uint32_t* tile_counters = nullptr;  // [64]
   int next_counter = 0;
   int gen = 0;
-  int variant = 0;   // partition tile shape (PartCfgA..D), LSB_PT_VARIANT
+  int variant = 0;   // partition tile shape (PartCfgA..F, 6 = persistent kernel), LSB_PT_VARIANT
+  int num_sms = 148;
   int tile = 0;      // elements per partition tile
   unsigned long long* hist = nullptr;        // [HIST_MAX_SUB][256]
   int64_t* scan_out = nullptr;               // [HIST_MAX_SUB][257]
@@ -68,6 +69,9 @@ struct lsb_ctx {
   unsigned long long* counts_all = nullptr;    // [G][65536]
   int64_t* mybase = nullptr;                 // [65536]
   int64_t* localbase = nullptr;              // [65536]
+  unsigned long long* next_hist = nullptr;     // [G][2][256] counted by the exchange kernel
+  unsigned long long* next_hist_all = nullptr; // [G][G][2][256]
+  int hist_ready_digit = -1;                 // digit whose sub-digit histograms already sit in hist[]
   uint32_t* seg_tile_start = nullptr;        // [257]
   int64_t* one_seg_start = nullptr;          // {0, here}
   uint32_t* one_seg_tiles = nullptr;         // {0, ceil(here/TILE)}
@@ -305,6 +309,12 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
 #define LSB_PART(CFG)                                                                                         \
     if (runs) partition_kernel<CFG, true><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a);     \
     else partition_kernel<CFG, false><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a)
+    if (c->variant == 6) {  // persistent kernel: one CTA per SM, single-segment inputs only
+      if (seg_bits) return fail(c, LSB_ERR_STATE, "persistent partition kernel needs a single segment");
+      const unsigned grid = (unsigned)std::min<int64_t>(c->num_sms, div_ceil(c->here, c->tile));
+      if (runs) partition_persistent_kernel<PersistCfgA, true><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
+      else partition_persistent_kernel<PersistCfgA, false><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
+    } else
     switch (c->variant) {
       case 0: LSB_PART(PartCfgA); break;
       case 1: LSB_PART(PartCfgB); break;
@@ -413,7 +423,7 @@ int pass_global_direct(lsb_ctx* c, int digit, int* subpasses) {
 //      counts of the full digit from the runs it writes (== counts, :226-229);
 //   3. count all-gather + digit-major/rank-minor scan (== :327-479);
 //   4. exchange kernel: every run goes to its global position in the owning GPU's shard (== :530-576).
-int pass_global(lsb_ctx* c, int digit, int* subpasses) {
+int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
   if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) return pass_global_direct(c, digit, subpasses);
   const PassPlan p = plan_pass(c, digit);
   const int nb = 1 << p.bits;
@@ -422,7 +432,14 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
   int ns = 0;
   if (p.lo_bits) subs[ns++] = {p.shift, p.lo_bits};
   subs[ns++] = {p.shift + p.lo_bits, p.hi_bits};
-  if ((rc = launch_hist(c, c->buf[c->cur], subs, ns))) return rc;
+  if (c->hist_ready_digit == digit) {  // the previous pass's exchange already counted this pass's sub-digits
+    scan256_kernel<<<ns, 256, 0, c->stream>>>(c->hist, c->scan_out);
+    c->launches++;
+    CU(c, cudaGetLastError());
+  } else if ((rc = launch_hist(c, c->buf[c->cur], subs, ns))) {
+    return rc;
+  }
+  c->hist_ready_digit = -1;
   CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
   for (int s = 0; s < ns; s++) {
     const bool last = (s == ns - 1);
@@ -451,6 +468,14 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
   if ((rc = global_offsets(c, nb))) return rc;
   if ((rc = phase_mark(c, 1))) return rc;
   const int xbuf = c->cur ^ 1;
+  SubPass nsubs[2];
+  int next_ns = 0;
+  if (fuse_next && digit + 1 < c->npasses) {
+    const PassPlan q = plan_pass(c, digit + 1);
+    if (q.lo_bits) nsubs[next_ns++] = {q.shift, q.lo_bits};
+    nsubs[next_ns++] = {q.shift + q.lo_bits, q.hi_bits};
+    CU(c, cudaMemsetAsync(c->next_hist, 0, sizeof(unsigned long long) * 512 * c->G, c->stream));
+  }
   if (c->here > 0) {
     ExchArgs x;
     memset(&x, 0, sizeof(x));
@@ -463,14 +488,35 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses) {
     x.per = c->per;
     x.world = c->G;
     for (int g = 0; g < c->G; g++) x.dst[g] = c->peer[xbuf][g];
+    if (next_ns) {
+      x.next_nsub = next_ns;
+      for (int s = 0; s < next_ns; s++) {
+        x.next_shift[s] = nsubs[s].shift;
+        x.next_mask[s] = (1u << nsubs[s].bits) - 1;
+      }
+      x.next_hist = c->next_hist;
+    }
     const int grid = (int)std::min<int64_t>(148 * 8, div_ceil(c->here, (int64_t)EX_THREADS * EX_U));
     exchange_kernel<<<grid, EX_THREADS, 0, c->stream>>>(x);
     c->launches++;
     CU(c, cudaGetLastError());
   }
   if ((rc = phase_mark(c, 3))) return rc;
-  // peers' stores into my shard must have landed before anything reads it
-  if ((rc = stream_barrier(c))) return rc;
+  if (next_ns) {
+    // all-gather of the per-destination counts: also the barrier "all peers' stores into my shard landed"
+    if (c->G > 1) {
+      NC(c, g_nccl.AllGather(c->next_hist, c->next_hist_all, (size_t)512 * c->G, ncclUint64, c->comm, c->stream));
+    } else {
+      CU(c, cudaMemcpyAsync(c->next_hist_all, c->next_hist, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    next_hist_reduce_kernel<<<1, 512, 0, c->stream>>>(c->next_hist_all, c->G, c->my, c->hist);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    c->hist_ready_digit = digit + 1;
+    if ((rc = phase_mark(c, 1))) return rc;
+  } else if ((rc = stream_barrier(c))) {  // peers' stores into my shard must have landed before anything reads it
+    return rc;
+  }
   c->cur = xbuf;
   return LSB_OK;
 }
@@ -590,8 +636,10 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   {
     const char* v = getenv("LSB_PT_VARIANT");
     c->variant = v ? atoi(v) : 4;  // PartCfgE measured fastest on B200 (profiles/)
-    if (c->variant < 0 || c->variant > 5) c->variant = 4;
-    const int tiles[6] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE, PartCfgE::TILE, PartCfgF::TILE};
+    if (c->variant < 0 || c->variant > 6) c->variant = 4;
+    if (c->variant == 6 && (cfg->flags & LSB_FLAG_DIRECT_SCATTER)) c->variant = 4;  // segmented input
+    const int tiles[7] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE, PartCfgE::TILE, PartCfgF::TILE,
+                          PersistCfgA::TILE};
     c->tile = tiles[c->variant];
   }
   c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
@@ -604,6 +652,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
   CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
   CUC(cudaMalloc(&c->localbase, sizeof(int64_t) * 65536));
+  CUC(cudaMalloc(&c->next_hist, sizeof(unsigned long long) * 512 * LSB_MAX_GPUS));
+  CUC(cudaMalloc(&c->next_hist_all, sizeof(unsigned long long) * 512 * LSB_MAX_GPUS * LSB_MAX_GPUS));
   CUC(cudaMalloc(&c->seg_tile_start, sizeof(uint32_t) * 257));
   CUC(cudaMalloc(&c->one_seg_start, sizeof(int64_t) * 2));
   CUC(cudaMalloc(&c->one_seg_tiles, sizeof(uint32_t) * 2));
@@ -627,6 +677,9 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   LSB_SET_ATTR(PartCfgD)
   LSB_SET_ATTR(PartCfgE)
   LSB_SET_ATTR(PartCfgF)
+  CUC(cudaFuncSetAttribute(partition_persistent_kernel<PersistCfgA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfgA::SMEM));
+  CUC(cudaFuncSetAttribute(partition_persistent_kernel<PersistCfgA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfgA::SMEM));
+  CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
 #undef LSB_SET_ATTR
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
@@ -653,6 +706,8 @@ void lsb_destroy(lsb_ctx* c) {
   cudaFree(c->counts_all);
   cudaFree(c->mybase);
   cudaFree(c->localbase);
+  cudaFree(c->next_hist);
+  cudaFree(c->next_hist_all);
   cudaFree(c->seg_tile_start);
   cudaFree(c->one_seg_start);
   cudaFree(c->one_seg_tiles);
@@ -739,6 +794,7 @@ int lsb_digit_bits(const lsb_ctx* c, int digit) {
 
 int lsb_generate(lsb_ctx* c) {
   if (!c) return LSB_ERR_ARG;
+  c->hist_ready_digit = -1;
   CU(c, cudaSetDevice(c->cfg.device));
   c->cur = 0;
   if (c->here > 0) {
@@ -766,6 +822,7 @@ int lsb_generate(lsb_ctx* c) {
 }
 
 int lsb_upload(lsb_ctx* c, const lsb_elt* host, int64_t off, int64_t count) {
+  if (c) c->hist_ready_digit = -1;
   if (!c || (!host && count) || off < 0 || count < 0 || off + count > c->per) return fail(c, LSB_ERR_ARG, "lsb_upload: range");
   CU(c, cudaSetDevice(c->cfg.device));
   if (count) CU(c, cudaMemcpyAsync(c->buf[c->cur] + off, host, (size_t)count * sizeof(Elt), cudaMemcpyHostToDevice, c->stream));
@@ -804,12 +861,13 @@ int lsb_sort(lsb_ctx* c, lsb_stats* st) {
   if (rc) return rc;
   CU(c, cudaSetDevice(c->cfg.device));
   if ((rc = begin_call(c))) return rc;
+  c->hist_ready_digit = -1;
   int subpasses = 0;
   if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) {
     if ((rc = passes_single(c, 0, c->npasses, &subpasses))) return rc;
   } else {
     for (int d = 0; d < c->npasses; d++)
-      if ((rc = pass_global(c, d, &subpasses))) return rc;
+      if ((rc = pass_global(c, d, &subpasses, true))) return rc;
   }
   return end_call(c, st, c->npasses, subpasses);
 }
@@ -822,7 +880,7 @@ int lsb_pass(lsb_ctx* c, int digit, lsb_stats* st) {
   if ((rc = begin_call(c))) return rc;
   int subpasses = 0;
   if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) rc = passes_single(c, digit, digit + 1, &subpasses);
-  else rc = pass_global(c, digit, &subpasses);
+  else rc = pass_global(c, digit, &subpasses, false);
   if (rc) return rc;
   return end_call(c, st, 1, subpasses);
 }

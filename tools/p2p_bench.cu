@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
 
@@ -38,9 +39,81 @@ __global__ void scatter_frontier(const Elt* __restrict__ src, Elt* dst, Elt* dst
   }
 }
 
+// same, with L2 eviction-priority hints: mode bit0 = loads evict_first, bit1 = stores evict_last,
+// bit2 = stores evict_first
+__global__ void scatter_frontier_hint(const Elt* __restrict__ src, Elt* dst, int64_t n, int T, int mode) {
+  const int run = T / 256;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t region = n / 256;
+  uint64_t pol_first, pol_last;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t tile = i / T;
+    const int p = (int)(i - tile * T);
+    const int bin = p / run, off = p - bin * run;
+    if (bin >= 256) continue;
+    Elt e;
+    if (mode & 1) asm volatile("ld.global.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(e.k), "=l"(e.v) : "l"(src + i), "l"(pol_first));
+    else e = src[i];
+    Elt* out = dst + bin * region + tile * run + off;
+    if (mode & 2) asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(out), "l"(e.k), "l"(e.v), "l"(pol_last) : "memory");
+    else if (mode & 4) asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(out), "l"(e.k), "l"(e.v), "l"(pol_first) : "memory");
+    else asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(out), "l"(e.k), "l"(e.v) : "memory");
+  }
+}
+
 int main(int argc, char** argv) {
   int nd = 0;
   CK(cudaGetDeviceCount(&nd));
+  if (argc > 2 && !strcmp(argv[2], "local")) {
+    // single GPU: how fast can HBM take the sort's write pattern (256 frontiers, T/256-element runs)
+    // next to a sequential read?  (upper bound for one partition launch)
+    const int64_t n = 1LL << atoi(argv[1]);
+    Elt *src, *dst;
+    CK(cudaMalloc(&src, n * sizeof(Elt)));
+    CK(cudaMalloc(&dst, (n + 64) * sizeof(Elt)));
+    CK(cudaMemset(src, 1, n * sizeof(Elt)));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    const int Ts[] = {2048, 2816, 3840, 4096, 5120, 5632, 6144, 7680, 8192, 8448, 11264, 12288, 16384, 16640};
+    for (int T : Ts) {
+      float ms = 0;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(a));
+        scatter_frontier<<<148 * 8, 512>>>(src, dst, dst, n, T);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&ms, a, b));
+      }
+      printf("local frontier pattern T=%d (run %d el = %d B): %.2f ms, %.0f GB/s read+write\n", T, T / 256, T / 16, ms,
+             n * 32.0 / ms / 1e6);
+    }
+    for (int mode = 0; mode < 8; mode++) {
+      if ((mode & 6) == 6) continue;
+      float ms = 0;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(a));
+        scatter_frontier_hint<<<148 * 8, 512>>>(src, dst, n, 5632, mode);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&ms, a, b));
+      }
+      printf("T=5632 hints: loads %s, stores %s: %.2f ms, %.0f GB/s read+write\n", (mode & 1) ? "evict_first" : "default",
+             (mode & 2) ? "evict_last" : (mode & 4) ? "evict_first" : "default", ms, n * 32.0 / ms / 1e6);
+    }
+    float ms = 0;
+    for (int rep = 0; rep < 3; rep++) {
+      CK(cudaEventRecord(a));
+      CK(cudaMemcpyAsync(dst, src, n * sizeof(Elt), cudaMemcpyDeviceToDevice));
+      CK(cudaEventRecord(b));
+      CK(cudaEventSynchronize(b));
+      CK(cudaEventElapsedTime(&ms, a, b));
+    }
+    printf("cudaMemcpy D2D: %.2f ms, %.0f GB/s read+write\n", ms, n * 32.0 / ms / 1e6);
+    return 0;
+  }
   if (nd < 2) { printf("needs 2 GPUs\n"); return 0; }
   const int64_t n = 1LL << (argc > 1 ? atoi(argv[1]) : 27);
   Elt *src, *local, *remote;
