@@ -63,6 +63,30 @@ __global__ void scatter_frontier_hint(const Elt* __restrict__ src, Elt* dst, int
   }
 }
 
+// same pattern, but every warp store instruction covers a 512-byte ALIGNED window of the destination
+// (lanes outside the run idle), so a 128-byte line inside a run is never split between two instructions
+__global__ void scatter_frontier_aligned(const Elt* __restrict__ src, Elt* dst, int64_t n, int T) {
+  const int run = T / 256;
+  const int64_t region = n / 256;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t nruns = (n / T) * 256;
+  for (int64_t r = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); r < nruns; r += nwarps) {
+    const int64_t tile = r >> 8;
+    const int bin = (int)(r & 255);
+    const int64_t s0 = tile * T + (int64_t)bin * run;        // first source element of the run
+    const int64_t g0 = bin * region + tile * run;            // first destination element
+    const int64_t g1 = g0 + run;
+    for (int64_t w = g0 & ~31LL; w < g1; w += 32) {
+      const int64_t g = w + lane;
+      if (g >= g0 && g < g1) {
+        Elt e = src[s0 + (g - g0)];
+        asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + g), "l"(e.k), "l"(e.v) : "memory");
+      }
+    }
+  }
+}
+
 int main(int argc, char** argv) {
   int nd = 0;
   CK(cudaGetDeviceCount(&nd));
@@ -89,6 +113,18 @@ int main(int argc, char** argv) {
       }
       printf("local frontier pattern T=%d (run %d el = %d B): %.2f ms, %.0f GB/s read+write\n", T, T / 256, T / 16, ms,
              n * 32.0 / ms / 1e6);
+    }
+    for (int T : {2816, 5632, 8448, 11264}) {
+      float ms = 0;
+      for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(a));
+        scatter_frontier_aligned<<<148 * 8, 512>>>(src, dst, n, T);
+        CK(cudaEventRecord(b));
+        CK(cudaEventSynchronize(b));
+        CK(cudaEventElapsedTime(&ms, a, b));
+      }
+      printf("destination-aligned warp windows, T=%d (run %d el): %.2f ms, %.0f GB/s read+write\n", T, T / 256, ms,
+             (n / T) * T * 32.0 / ms / 1e6);
     }
     for (int mode = 0; mode < 8; mode++) {
       if ((mode & 6) == 6) continue;
