@@ -174,12 +174,16 @@ def main_cuda(args, rank, world, local_rank):
 
     per_gpu_log2 = args.log2n if args.log2n else (30 if world == 1 else 31)
     n = world << per_gpu_log2
-    sorter = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=local_rank,
-                                   radix_bits=args.radix, flags=L.FLAG_PHASE_EVENTS if args.phases else 0)
-    if world > 1:
-        ids = [lsb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        sorter.comm_init(ids[0])
+    def make_sorter(n_total, flags):
+        s_ = lsb.DistributedSorter(n_total, ranks=world, world_size=world, world_rank=rank, device=local_rank,
+                                   radix_bits=args.radix, flags=flags)
+        if world > 1:
+            ids = [lsb.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            s_.comm_init(ids[0])
+        return s_
+
+    sorter = make_sorter(n, L.FLAG_PHASE_EVENTS if args.phases else 0)
 
     # ---- warm-up (also the correctness gate: a wrong sort is not a benchmark) ----
     for w in range(args.warmup):
@@ -211,12 +215,7 @@ def main_cuda(args, rank, world, local_rank):
 
     # ---- per-kernel durations for the roofline (phase events; separate, untimed-for-value step) ----
     sorter.close()
-    sorter = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=local_rank,
-                                   radix_bits=args.radix, flags=L.FLAG_PHASE_EVENTS)
-    if world > 1:
-        ids = [lsb.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        sorter.comm_init(ids[0])
+    sorter = make_sorter(n, L.FLAG_PHASE_EVENTS)
     kp_ms, kp_n, hist_ms = [], 0, []
     for _ in range(max(2, min(args.steps, 3))):
         sorter.generate()
@@ -245,24 +244,50 @@ def main_cuda(args, rank, world, local_rank):
             traffic = json.load(f).get("dram_bytes_per_element", 0) * here or None  # per launch of `here` elements
 
     # ---- end to end through the host-buffer C-ABI entry point ----
+    # Every rank pins an input and an output buffer for its whole shard; if the host cannot hold
+    # 2 x 16 B x n (8 ranks x 2^31 elements = 512 GiB), the e2e leg drops to the largest power of two
+    # per GPU that fits and says so.
     e2e = None
     if not args.no_e2e:
-        sorter.generate()
-        hin, hout = L.PinnedBuffer(here), L.PinnedBuffer(here)
-        sorter.download(out=hin.array)
+        def mem_available():
+            try:
+                with open("/proc/meminfo") as f:
+                    for line in f:
+                        if line.startswith("MemAvailable:"):
+                            return int(line.split()[1]) * 1024
+            except OSError:
+                pass
+            return 1 << 62
+        e2e_log2 = per_gpu_log2
+        while e2e_log2 > 20 and 2 * 16 * (world << e2e_log2) * 1.15 > mem_available():
+            e2e_log2 -= 1
+        if world > 1:  # all ranks must agree
+            t = torch.tensor([e2e_log2], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            e2e_log2 = int(t.item())
+        es = sorter
+        if e2e_log2 != per_gpu_log2:
+            sorter.close()
+            es = sorter = make_sorter(world << e2e_log2, 0)
+        e_n, e_here = world << e2e_log2, es.here
+        es.generate()
+        hin, hout = L.PinnedBuffer(e_here), L.PinnedBuffer(e_here)
+        es.download(out=hin.array)
         walls = []
         for i in range(1 + args.e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            sorter.sort_host(hin.array, hout.array)
+            es.sort_host(hin.array, hout.array)
             barrier()
             if i:  # first one is warm-up
                 walls.append(max_over_ranks(time.perf_counter() - t0))
-        ok = bool((hout.array["key"][:-1] <= hout.array["key"][1:]).all()) if here < (1 << 27) else \
-            bool((hout.array["key"][:1 << 20][:-1] <= hout.array["key"][:1 << 20][1:]).all())
-        e2e = {"value": n / statistics.mean(walls) / 1e6, "unit": UNIT, "h2d_bytes_per_step": here * 16 * world,
-               "d2h_bytes_per_step": here * 16 * world, "ms_per_step": 1e3 * statistics.mean(walls),
-               "api": "lsb_sort_host (pinned host in/out)", "output_sorted": ok}
+        chk = min(e_here, 1 << 20)
+        ok = bool((hout.array["key"][:chk][:-1] <= hout.array["key"][:chk][1:]).all())
+        e2e = {"value": e_n / statistics.mean(walls) / 1e6, "unit": UNIT, "h2d_bytes_per_step": e_here * 16 * world,
+               "d2h_bytes_per_step": e_here * 16 * world, "ms_per_step": 1e3 * statistics.mean(walls),
+               "api": "lsb_sort_host (pinned host in/out)", "output_sorted": ok, "n_total": e_n}
+        if e2e_log2 != per_gpu_log2:
+            e2e["note"] = f"host memory holds 2^{e2e_log2} elements per GPU for the pinned in/out buffers, not 2^{per_gpu_log2}"
         hin.free()
         hout.free()
     sorter.close()

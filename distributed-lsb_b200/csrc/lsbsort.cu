@@ -150,7 +150,7 @@ PassPlan plan_pass(const lsb_ctx* c, int digit) {
   PassPlan p;
   p.shift = c->cfg.radix_bits * digit;
   p.bits = std::min<int>(c->cfg.radix_bits, 64 - p.shift);
-  p.lo_bits = p.bits > 8 ? p.bits - 8 : 0;
+  p.lo_bits = p.bits > 8 ? p.bits / 2 : 0;  // balanced split: fewer bins per step = longer runs per bin
   p.hi_bits = p.bits - p.lo_bits;
   return p;
 }

@@ -41,7 +41,7 @@ def plan_pass(radix_bits, digit):
     sorted as a stable low-sub-digit step followed by a stable high-sub-digit step"""
     shift = radix_bits * digit
     bits = min(radix_bits, 64 - shift)
-    lo = bits - 8 if bits > 8 else 0
+    lo = bits // 2 if bits > 8 else 0  # balanced split: fewer bins per step = longer runs per bin
     return shift, bits, lo, bits - lo
 
 
