@@ -986,8 +986,14 @@ typedef PersistCfg<7> PersistCfgA;  // 5376-element tiles, 2 x 84 KiB stages, 19
 // TLB set conflicts on cross-process peer mappings) when the 22-element runs of the scatter
 // kernel are stored remotely (tools/p2p_bench.cu, tools/p2p_ipc_bench.cu).
 // ------------------------------------------------------------------------------------
-constexpr int EX_THREADS = 512;
-constexpr int EX_U = 4;
+#ifndef LSB_EX_THREADS
+#define LSB_EX_THREADS 512
+#endif
+#ifndef LSB_EX_U
+#define LSB_EX_U 4
+#endif
+constexpr int EX_THREADS = LSB_EX_THREADS;
+constexpr int EX_U = LSB_EX_U;
 
 struct ExchArgs {
   const Elt* src;

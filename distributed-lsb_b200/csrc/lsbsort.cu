@@ -496,7 +496,8 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
       }
       x.next_hist = c->next_hist;
     }
-    const int grid = (int)std::min<int64_t>(148 * 8, div_ceil(c->here, (int64_t)EX_THREADS * EX_U));
+    static const int ex_mult = getenv("LSB_EX_GRID") ? atoi(getenv("LSB_EX_GRID")) : 8;  // CTAs per SM worth of grid
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * ex_mult, div_ceil(c->here, (int64_t)EX_THREADS * EX_U));
     exchange_kernel<<<grid, EX_THREADS, 0, c->stream>>>(x);
     c->launches++;
     CU(c, cudaGetLastError());
