@@ -255,3 +255,25 @@ def test_cpp_driver_exit_code_and_knobs():
     assert rc == 0 and "Verifying" in out and "Verification FAILED" not in out
     rc, out = _run_driver("--n", "1000", "--no-verify")
     assert rc == 0 and "Verifying" not in out
+
+
+def test_randomised_parity_sweep():
+    """seeded sweep over n / streams / digit width / skew / pass shape; every case bit-exact vs the oracle"""
+    rng = np.random.default_rng(20261018)
+    masks = [ALL, 0xFFFFFF, 0xFFFF0000FFFF0000, 0xF0F0F0F0F0F0F0F0, 0x3FF, 1 << 63]
+    for case in range(40):
+        n = int(rng.integers(0, 60000)) if case % 4 else int(rng.integers(5000, 400000))
+        R = int(rng.integers(1, 9))
+        bits = int(rng.choice([1, 3, 5, 7, 8, 9, 10, 11, 12, 14, 15, 16])) if case % 3 == 0 else 16
+        mask = masks[int(rng.integers(0, len(masks)))]
+        k = int(rng.integers(1, 4))
+        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_DIRECT_SCATTER][case % 4]
+        if bits < 4 and n > 20000:
+            n = 20000  # 64 passes of a 1-bit digit: keep the oracle quick
+        g = O.generate(n, R, key_mask=mask, and_draws=k)
+        want = O.sort(g, n, R, bits)
+        with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, key_mask=mask, and_draws=k, flags=flags) as s:
+            s.generate()
+            s.my_sort()
+            got = s.download()
+        assert (got == want).all(), (case, n, R, bits, hex(mask), k, flags)
