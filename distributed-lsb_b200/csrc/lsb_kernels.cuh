@@ -1074,6 +1074,194 @@ __global__ void __launch_bounds__(512) next_hist_reduce_kernel(const unsigned lo
 }
 
 // ------------------------------------------------------------------------------------
+// Pipelined multi-GPU pass ("virtual ranks"): every shard is cut into V contiguous parts and
+// part q of GPU g acts as rank g*V+q of the reference's algorithm (its order is the global
+// index order, so the result is unchanged).  Once the counts of the pass's full digit are known
+// for every virtual rank BEFORE the pass starts, part q can be sorted locally and exchanged
+// while part q+1 is being sorted: the NVLink time hides the local HBM time.  The counts of
+// pass p+1 are produced by the exchange kernel of pass p (one L2 atomic per element, hidden
+// under the NVLink time), per destination GPU and destination part.
+// ------------------------------------------------------------------------------------
+
+// counts[d] += 1 for a range (first pass only: nothing has counted this digit yet)
+__global__ void dense_count32_kernel(const Elt* src, int64_t m, int shift, uint32_t mask, unsigned* out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
+    atomicAdd(out + ((unsigned)(ld_stream_key(src + i) >> shift) & mask), 1u);
+}
+
+// global_scan_kernel for virtual ranks: counts[vr][d] (u32), scan in digit-major, virtual-rank-minor
+// order; mybase[q][d] for this GPU's V parts (vr = first_vr + q), sent[] summed over the parts
+struct VrScanArgs {
+  const unsigned* counts;  // [GV][nb]
+  int32_t nb, GV, first_vr, V, G;
+  int64_t per;             // destination shard size
+  int64_t* mybase;         // [V][nb]
+  unsigned long long* sent;  // [G], caller zeroes (may be null)
+};
+
+__global__ void __launch_bounds__(1024) vr_scan_kernel(const VrScanArgs a) {
+  __shared__ uint64_t wtot[32];
+  __shared__ unsigned long long s_sent[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t < 8) s_sent[t] = 0;
+  const int chunk = (a.nb + 1023) / 1024;
+  const int d0 = t * chunk, d1 = min(d0 + chunk, a.nb);
+  uint64_t local = 0;
+  for (int vr = 0; vr < a.GV; vr++)
+    for (int d = d0; d < d1; d++) local += a.counts[(size_t)vr * a.nb + d];
+  const uint64_t incl = warp_incl_scan(local);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t run = incl - local;
+  for (int i = 0; i < w; i++) run += wtot[i];
+  unsigned long long sent[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int d = d0; d < d1; d++)
+    for (int vr = 0; vr < a.GV; vr++) {
+      const uint64_t c = a.counts[(size_t)vr * a.nb + d];
+      const int q = vr - a.first_vr;
+      if (q >= 0 && q < a.V) {
+        a.mybase[(size_t)q * a.nb + d] = (int64_t)run;
+        if (c && a.sent) {
+          uint64_t b = run, e = run + c;
+          while (b < e) {
+            const uint64_t r = b / (uint64_t)a.per;
+            const uint64_t lim = (r + 1) * (uint64_t)a.per;
+            const uint64_t x = e < lim ? e : lim;
+            sent[r] += x - b;
+            b = x;
+          }
+        }
+      }
+      run += c;
+    }
+  if (a.sent) {
+    for (int g = 0; g < a.G; g++)
+      if (sent[g]) atomicAdd(&s_sent[g], sent[g]);
+    __syncthreads();
+    if (t < a.G) a.sent[t] = s_sent[t];
+  }
+}
+
+// one block per part: where each digit's run starts inside the sorted part (localbase), and the
+// bases of the two local counting-sort steps (sub-digit histograms folded out of the dense counts)
+struct PartPrepArgs {
+  const unsigned* counts;  // [V][nb] this GPU's parts
+  int32_t nb, lo_bits, hi_bits;
+  int64_t* localbase;      // [V][nb]
+  int64_t* bases;          // [V][2][257]: exclusive scans of the low / high sub-digit counts (+ total)
+};
+
+__global__ void __launch_bounds__(1024) part_prep_kernel(const PartPrepArgs a) {
+  __shared__ uint64_t wtot[32];
+  __shared__ unsigned long long s_lo[256], s_hi[256];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned* c = a.counts + (size_t)blockIdx.x * a.nb;
+  int64_t* lb = a.localbase + (size_t)blockIdx.x * a.nb;
+  if (t < 256) { s_lo[t] = 0; s_hi[t] = 0; }
+  __syncthreads();
+  const int chunk = (a.nb + 1023) / 1024;
+  const int d0 = t * chunk, d1 = min(d0 + chunk, a.nb);
+  const unsigned lo_mask = (1u << a.lo_bits) - 1;
+  uint64_t local = 0;
+  for (int d = d0; d < d1; d++) {
+    const unsigned v = c[d];
+    local += v;
+    if (v) {
+      if (a.lo_bits) atomicAdd(&s_lo[d & lo_mask], (unsigned long long)v);
+      atomicAdd(&s_hi[d >> a.lo_bits], (unsigned long long)v);
+    }
+  }
+  const uint64_t incl = warp_incl_scan(local);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t run = incl - local;
+  for (int i = 0; i < w; i++) run += wtot[i];
+  for (int d = d0; d < d1; d++) {
+    lb[d] = (int64_t)run;
+    run += c[d];
+  }
+  __syncthreads();
+  // exclusive scans of the two 256-bin histograms by warps 0 and 1 (8 bins per lane)
+  if (w < 2) {
+    unsigned long long* h = w ? s_hi : s_lo;
+    int64_t* out = a.bases + ((size_t)blockIdx.x * 2 + w) * 257;
+    unsigned long long v[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { v[i] = h[lane * 8 + i]; sum += v[i]; }
+    const uint64_t inc = warp_incl_scan(sum);
+    uint64_t r = inc - sum;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { out[lane * 8 + i] = (int64_t)r; r += v[i]; }
+    if (lane == 31) out[256] = (int64_t)r;
+  }
+}
+
+// exchange of one sorted part (see exchange_kernel) that also counts the next pass's full digit per
+// (destination GPU, destination part): next_dense[(r*V + v)][d'] += 1
+struct ExchVrArgs {
+  const Elt* src;
+  int64_t m;
+  int32_t shift;
+  uint32_t mask;
+  const int64_t* localbase;
+  const int64_t* mybase;
+  int64_t per;
+  int32_t world;
+  Elt* dst[8];
+  int32_t has_next, next_shift;
+  uint32_t next_mask;
+  int32_t V, next_nb;
+  int64_t part;            // elements per destination part (the last part may be shorter)
+  unsigned* next_dense;    // [G][V][next_nb]
+};
+
+__global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArgs a) {
+  __shared__ Elt* s_dst[8];
+  __shared__ long long s_lim[8];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      s_dst[q] = a.dst[q];
+      s_lim[q] = (long long)q * a.per;
+    }
+  }
+  __syncthreads();
+  const int64_t chunk = (int64_t)EX_THREADS * EX_U;
+  const int64_t span = ((a.m + a.world - 1) / a.world + chunk - 1) / chunk * chunk;
+  const int64_t chunks_per_span = span / chunk;
+  const int64_t total = chunks_per_span * a.world;
+  for (int64_t k = blockIdx.x; k < total; k += gridDim.x) {
+    const int64_t c0 = (k % a.world) * span + (k / a.world) * chunk;
+    if (c0 >= a.m) continue;
+    Elt e[EX_U];
+#pragma unroll
+    for (int u = 0; u < EX_U; u++) {
+      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
+      if (i < a.m) e[u] = ld_stream(a.src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < EX_U; u++) {
+      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
+      if (i < a.m) {
+        const unsigned d = (unsigned)(e[u].key >> a.shift) & a.mask;
+        const long long g = __ldg(a.mybase + d) + (i - __ldg(a.localbase + d));
+        int r = 0;
+        for (int q = 1; q < a.world; q++) r += (g >= s_lim[q]);
+        const long long j = g - s_lim[r];
+        st_elt(s_dst[r] + j, e[u]);
+        if (a.has_next) {
+          int v = (int)(j / a.part);
+          v = v < a.V ? v : a.V - 1;
+          const unsigned dn = (unsigned)(e[u].key >> a.next_shift) & a.next_mask;
+          atomicAdd(a.next_dense + ((size_t)(r * a.V + v) * a.next_nb + dn), 1u);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // verification: strictly increasing (key,val) + multiset hash (mpi/mpi_lsbsort.cpp:710-739)
 // ------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t mix64(uint64_t k, uint64_t v) {

@@ -72,6 +72,24 @@ struct lsb_ctx {
   unsigned long long* next_hist = nullptr;     // [G][2][256] counted by the exchange kernel
   unsigned long long* next_hist_all = nullptr; // [G][G][2][256]
   int hist_ready_digit = -1;                 // digit whose sub-digit histograms already sit in hist[]
+  // pipelined pass (virtual ranks): shard cut into V parts
+  bool pipelined = false;
+  int V = 4;
+  int64_t vpart = 0;                         // elements per part
+  Elt* scratch[2] = {nullptr, nullptr};      // part-sized scratch for the local sort of one part
+  unsigned* dense_local = nullptr;           // [V][65536] counts of the full digit per part (first pass)
+  unsigned* next_dense = nullptr;            // [G][V][65536] counted by the exchange kernel for the next pass
+  unsigned* dense_mine = nullptr;            // [V][65536] after the reduce-scatter
+  unsigned* c_all = nullptr;                 // [G*V][65536] counts of every virtual rank
+  int64_t* mybase_v = nullptr;               // [V][65536]
+  int64_t* localbase_v = nullptr;            // [V][65536]
+  int64_t* bases_v = nullptr;                // [V][2][257]
+  int64_t* seg_start_v = nullptr;            // [V][2] = {0, m_q}
+  uint32_t* seg_tiles_v = nullptr;           // [V][2] = {0, tiles of part q}
+  int dense_ready_digit = -1;                // digit whose dense counts already sit in c_all
+  cudaStream_t xstream = nullptr;            // exchange stream (highest priority)
+  cudaEvent_t ev_sorted[8] = {}, ev_xs[8] = {}, ev_x[8] = {};
+  double exchange_ms_acc = 0;
   uint32_t* seg_tile_start = nullptr;        // [257]
   int64_t* one_seg_start = nullptr;          // {0, here}
   uint32_t* one_seg_tiles = nullptr;         // {0, ceil(here/TILE)}
@@ -103,6 +121,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   std::string error;
   bool load() {
@@ -118,6 +137,7 @@ struct NcclApi {
     LSB_SYM(CommDestroy, "ncclCommDestroy");
     LSB_SYM(AllGather, "ncclAllGather");
     LSB_SYM(AllReduce, "ncclAllReduce");
+    LSB_SYM(ReduceScatter, "ncclReduceScatter");
     LSB_SYM(GetErrorString, "ncclGetErrorString");
 #undef LSB_SYM
     return true;
@@ -172,7 +192,8 @@ int begin_call(lsb_ctx* c) {
   c->launches = 0;
   c->skipped = 0;
   c->next_counter = 0;
-  CU(c, cudaMemsetAsync(c->tile_counters, 0, 64 * sizeof(uint32_t), c->stream));
+  CU(c, cudaMemsetAsync(c->tile_counters, 0, 256 * sizeof(uint32_t), c->stream));
+  c->exchange_ms_acc = 0;
   CU(c, cudaEventRecord(c->ev_start, c->stream));
   return phase_mark(c, -1);
 }
@@ -207,6 +228,7 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
     }
   }
   st->partition_launches = subpasses;
+  if (c->exchange_ms_acc > 0) st->exchange_ms = c->exchange_ms_acc;
   if (c->G > 1) {
     CU(c, cudaMemcpy(c->host_small, c->small, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int g = 0; g < c->G; g++) st->sent[g] = (int64_t)c->host_small[g];
@@ -269,12 +291,12 @@ int launch_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
 
 int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bits, const int64_t* seg_start,
                      const uint32_t* seg_tile_start, const int64_t* bases, int dst_buf, bool global_dst,
-                     int full_shift = -1, int full_bits = 0) {
+                     int full_shift = -1, int full_bits = 0, int64_t m_override = -1, Elt* dst_override = nullptr) {
   if (c->gen > 126) {  // tags exhausted: wipe the look-back words and start over
     CU(c, cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
     c->gen = 0;
   }
-  if (c->next_counter >= 64) return fail(c, LSB_ERR_STATE, "too many partition launches in one call");
+  if (c->next_counter >= 256) return fail(c, LSB_ERR_STATE, "too many partition launches in one call");
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.src = src;
@@ -296,22 +318,24 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
   } else {
     a.per = INT64_MAX / 16;
     a.world = 1;
-    a.dst[0] = c->buf[dst_buf];
+    a.dst[0] = dst_override ? dst_override : c->buf[dst_buf];
   }
-  const int64_t max_tiles = div_ceil(c->here, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
-  if (c->here > 0) {
+  const int64_t m_launch = m_override >= 0 ? m_override : c->here;
+  const int64_t max_tiles = div_ceil(m_launch, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
+  if (m_launch > 0) {
     const bool runs = full_shift >= 0;
     if (runs) {
       a.run_counts = c->counts_local;
       a.full_shift = full_shift;
       a.full_mask = (1u << full_bits) - 1;
     }
+    static const int extra_smem = getenv("LSB_PT_EXTRA_SMEM") ? atoi(getenv("LSB_PT_EXTRA_SMEM")) : 0;  // experiment: force 1 CTA/SM
 #define LSB_PART(CFG)                                                                                         \
-    if (runs) partition_kernel<CFG, true><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a);     \
-    else partition_kernel<CFG, false><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM, c->stream>>>(a)
+    if (runs) partition_kernel<CFG, true><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM + extra_smem, c->stream>>>(a);     \
+    else partition_kernel<CFG, false><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM + extra_smem, c->stream>>>(a)
     if (c->variant == 6) {  // persistent kernel: one CTA per SM, single-segment inputs only
       if (seg_bits) return fail(c, LSB_ERR_STATE, "persistent partition kernel needs a single segment");
-      const unsigned grid = (unsigned)std::min<int64_t>(c->num_sms, div_ceil(c->here, c->tile));
+      const unsigned grid = (unsigned)std::min<int64_t>(c->num_sms, div_ceil(m_launch, c->tile));
       if (runs) partition_persistent_kernel<PersistCfgA, true><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
       else partition_persistent_kernel<PersistCfgA, false><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
     } else
@@ -423,8 +447,11 @@ int pass_global_direct(lsb_ctx* c, int digit, int* subpasses) {
 //      counts of the full digit from the runs it writes (== counts, :226-229);
 //   3. count all-gather + digit-major/rank-minor scan (== :327-479);
 //   4. exchange kernel: every run goes to its global position in the owning GPU's shard (== :530-576).
+int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next);
+
 int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
   if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) return pass_global_direct(c, digit, subpasses);
+  if (c->pipelined) return pass_global_pipelined(c, digit, subpasses, fuse_next);
   const PassPlan p = plan_pass(c, digit);
   const int nb = 1 << p.bits;
   int rc;
@@ -516,6 +543,145 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     c->hist_ready_digit = digit + 1;
     if ((rc = phase_mark(c, 1))) return rc;
   } else if ((rc = stream_barrier(c))) {  // peers' stores into my shard must have landed before anything reads it
+    return rc;
+  }
+  c->cur = xbuf;
+  return LSB_OK;
+}
+
+// one reference pass, multi-GPU, pipelined over V parts of the shard (virtual ranks g*V+q):
+//   counts of the full digit of every part are known up front (first pass: counted here; later
+//   passes: produced by the previous pass's exchange kernel), so
+//     part q:   local low step, local high step (compute stream)  ->  exchange (exchange stream)
+//   and the exchange of part q overlaps the local sort of part q+1.
+int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits;
+  const int V = c->V;
+  int rc;
+  auto part_len = [&](int q) { return std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart)); };
+
+  if (c->dense_ready_digit != digit) {  // nobody has counted this digit yet
+    CU(c, cudaMemsetAsync(c->dense_local, 0, sizeof(unsigned) * (size_t)V * nb, c->stream));
+    for (int q = 0; q < V; q++) {
+      const int64_t m = part_len(q);
+      if (m <= 0) continue;
+      dense_count32_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->buf[c->cur] + (int64_t)q * c->vpart, m, p.shift,
+                                                               (uint32_t)(nb - 1), c->dense_local + (size_t)q * nb);
+      c->launches++;
+    }
+    CU(c, cudaGetLastError());
+    if (c->G > 1) {
+      NC(c, g_nccl.AllGather(c->dense_local, c->c_all, (size_t)V * nb, ncclUint32, c->comm, c->stream));
+    } else {
+      CU(c, cudaMemcpyAsync(c->c_all, c->dense_local, sizeof(unsigned) * (size_t)V * nb, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if ((rc = phase_mark(c, 0))) return rc;
+  }
+  c->dense_ready_digit = -1;
+
+  CU(c, cudaMemsetAsync(c->small, 0, 8 * sizeof(unsigned long long), c->stream));
+  {
+    VrScanArgs v;
+    v.counts = c->c_all;
+    v.nb = nb;
+    v.GV = c->G * V;
+    v.first_vr = c->my * V;
+    v.V = V;
+    v.G = c->G;
+    v.per = c->per;
+    v.mybase = c->mybase_v;
+    v.sent = c->small;
+    vr_scan_kernel<<<1, 1024, 0, c->stream>>>(v);
+    PartPrepArgs pp;
+    pp.counts = c->c_all + (size_t)c->my * V * nb;
+    pp.nb = nb;
+    pp.lo_bits = p.lo_bits;
+    pp.hi_bits = p.hi_bits;
+    pp.localbase = c->localbase_v;
+    pp.bases = c->bases_v;
+    part_prep_kernel<<<V, 1024, 0, c->stream>>>(pp);
+    c->launches += 2;
+    CU(c, cudaGetLastError());
+  }
+  if ((rc = phase_mark(c, 1))) return rc;
+
+  int next_nb = 0, next_shift = 0;
+  const bool has_next = fuse_next && digit + 1 < c->npasses;
+  if (has_next) {
+    const PassPlan q = plan_pass(c, digit + 1);
+    next_nb = 1 << q.bits;
+    next_shift = q.shift;
+    CU(c, cudaMemsetAsync(c->next_dense, 0, sizeof(unsigned) * (size_t)c->G * V * next_nb, c->stream));
+  }
+  static const int ex_mult = getenv("LSB_EX_GRID_PIPE") ? atoi(getenv("LSB_EX_GRID_PIPE")) : 1;
+  const int xbuf = c->cur ^ 1;
+  int last_x = -1;
+  for (int q = 0; q < V; q++) {
+    const int64_t m = part_len(q);
+    if (m <= 0) continue;
+    Elt* part = c->buf[c->cur] + (int64_t)q * c->vpart;
+    const Elt* sorted = part;
+    const int64_t* segs = c->seg_start_v + 2 * q;
+    const uint32_t* tiles = c->seg_tiles_v + 2 * q;
+    if (p.lo_bits) {  // low step into the scratch, high step back in place
+      if ((rc = launch_partition(c, part, p.shift, p.lo_bits, 0, segs, tiles, c->bases_v + ((size_t)q * 2 + 0) * 257, 0, false,
+                                 -1, 0, m, c->scratch[0])))
+        return rc;
+      if ((rc = launch_partition(c, c->scratch[0], p.shift + p.lo_bits, p.hi_bits, 0, segs, tiles,
+                                 c->bases_v + ((size_t)q * 2 + 1) * 257, 0, false, -1, 0, m, part)))
+        return rc;
+      (*subpasses) += 2;
+    } else {  // a single step: its output lives in an alternating scratch until it has been exchanged
+      if (q >= 2 && last_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[q - 2], 0));
+      if ((rc = launch_partition(c, part, p.shift, p.hi_bits, 0, segs, tiles, c->bases_v + ((size_t)q * 2 + 1) * 257, 0, false,
+                                 -1, 0, m, c->scratch[q & 1])))
+        return rc;
+      sorted = c->scratch[q & 1];
+      (*subpasses)++;
+    }
+    CU(c, cudaEventRecord(c->ev_sorted[q], c->stream));
+    CU(c, cudaStreamWaitEvent(c->xstream, c->ev_sorted[q], 0));
+    CU(c, cudaEventRecord(c->ev_xs[q], c->xstream));
+    ExchVrArgs x;
+    memset(&x, 0, sizeof(x));
+    x.src = sorted;
+    x.m = m;
+    x.shift = p.shift;
+    x.mask = (uint32_t)(nb - 1);
+    x.localbase = c->localbase_v + (size_t)q * nb;
+    x.mybase = c->mybase_v + (size_t)q * nb;
+    x.per = c->per;
+    x.world = c->G;
+    for (int g = 0; g < c->G; g++) x.dst[g] = c->peer[xbuf][g];
+    x.has_next = has_next;
+    x.next_shift = next_shift;
+    x.next_mask = (uint32_t)(next_nb - 1);
+    x.V = V;
+    x.next_nb = next_nb;
+    x.part = c->vpart;
+    x.next_dense = c->next_dense;
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * ex_mult, div_ceil(m, (int64_t)EX_THREADS * EX_U));
+    exchange_vr_kernel<<<grid, EX_THREADS, 0, c->xstream>>>(x);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_x[q], c->xstream));
+    last_x = q;
+  }
+  if (last_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[last_x], 0));
+  if ((rc = phase_mark(c, 4))) return rc;
+  if (has_next) {
+    // sum the G contributions to each of my parts, then share every virtual rank's counts: the two
+    // collectives are also the barrier "all peers' stores into my shard have landed"
+    if (c->G > 1) {
+      NC(c, g_nccl.ReduceScatter(c->next_dense, c->dense_mine, (size_t)V * next_nb, ncclUint32, ncclSum, c->comm, c->stream));
+      NC(c, g_nccl.AllGather(c->dense_mine, c->c_all, (size_t)V * next_nb, ncclUint32, c->comm, c->stream));
+    } else {
+      CU(c, cudaMemcpyAsync(c->c_all, c->next_dense, sizeof(unsigned) * (size_t)V * next_nb, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->dense_ready_digit = digit + 1;
+    if ((rc = phase_mark(c, 1))) return rc;
+  } else if ((rc = stream_barrier(c))) {
     return rc;
   }
   c->cur = xbuf;
@@ -646,7 +812,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
   CUC(cudaMalloc(&c->lookback, c->lookback_tiles * 256 * sizeof(uint64_t)));
   CUC(cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
-  CUC(cudaMalloc(&c->tile_counters, 64 * sizeof(uint32_t)));
+  CUC(cudaMalloc(&c->tile_counters, 256 * sizeof(uint32_t)));
   CUC(cudaMalloc(&c->hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB));
   CUC(cudaMalloc(&c->scan_out, sizeof(int64_t) * 257 * HIST_MAX_SUB));
   CUC(cudaMalloc(&c->counts_local, sizeof(unsigned long long) * 65536));
@@ -658,6 +824,48 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->seg_tile_start, sizeof(uint32_t) * 257));
   CUC(cudaMalloc(&c->one_seg_start, sizeof(int64_t) * 2));
   CUC(cudaMalloc(&c->one_seg_tiles, sizeof(uint32_t) * 2));
+  {
+    const bool multi = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
+    c->pipelined = multi && !(cfg->flags & (LSB_FLAG_NO_PIPELINE | LSB_FLAG_DIRECT_SCATTER));
+    const char* v = getenv("LSB_VPARTS");
+    c->V = v ? atoi(v) : 4;
+    if (c->V < 1 || c->V > 8) c->V = 4;
+    c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
+  }
+  if (c->pipelined) {
+    const int V = c->V;
+    CUC(cudaMalloc(&c->scratch[0], (size_t)(c->vpart + 64) * sizeof(Elt)));
+    CUC(cudaMalloc(&c->scratch[1], (size_t)(c->vpart + 64) * sizeof(Elt)));
+    CUC(cudaMalloc(&c->dense_local, sizeof(unsigned) * 65536 * V));
+    CUC(cudaMalloc(&c->dense_mine, sizeof(unsigned) * 65536 * V));
+    CUC(cudaMalloc(&c->next_dense, sizeof(unsigned) * 65536 * V * c->G));
+    CUC(cudaMalloc(&c->c_all, sizeof(unsigned) * 65536 * V * c->G));
+    CUC(cudaMalloc(&c->mybase_v, sizeof(int64_t) * 65536 * V));
+    CUC(cudaMalloc(&c->localbase_v, sizeof(int64_t) * 65536 * V));
+    CUC(cudaMalloc(&c->bases_v, sizeof(int64_t) * 257 * 2 * V));
+    CUC(cudaMalloc(&c->seg_start_v, sizeof(int64_t) * 2 * V));
+    CUC(cudaMalloc(&c->seg_tiles_v, sizeof(uint32_t) * 2 * V));
+    int64_t segs[16];
+    uint32_t tls[16];
+    for (int q = 0; q < V; q++) {
+      const int64_t m = std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart));
+      segs[2 * q] = 0;
+      segs[2 * q + 1] = m;
+      tls[2 * q] = 0;
+      tls[2 * q + 1] = (uint32_t)div_ceil(m, c->tile);
+    }
+    CUC(cudaMemcpyAsync(c->seg_start_v, segs, sizeof(int64_t) * 2 * V, cudaMemcpyHostToDevice, c->stream));
+    CUC(cudaMemcpyAsync(c->seg_tiles_v, tls, sizeof(uint32_t) * 2 * V, cudaMemcpyHostToDevice, c->stream));
+    CUC(cudaStreamSynchronize(c->stream));
+    int lo_prio = 0, hi_prio = 0;
+    CUC(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    CUC(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi_prio));
+    for (int q = 0; q < 8; q++) {
+      CUC(cudaEventCreateWithFlags(&c->ev_sorted[q], cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->ev_xs[q], cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->ev_x[q], cudaEventDisableTiming));
+    }
+  }
   CUC(cudaMalloc(&c->small, sizeof(unsigned long long) * 64));
   CUC(cudaMalloc(&c->small_all, sizeof(unsigned long long) * 16 * LSB_MAX_GPUS));
   CUC(cudaMemsetAsync(c->small, 0, sizeof(unsigned long long) * 64, c->stream));
@@ -668,7 +876,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
   CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
 #define LSB_SET_ATTR(CFG)                                                                                   \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM)); \
+  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM + 8192)); \
   CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
   CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));  \
   CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -709,6 +917,23 @@ void lsb_destroy(lsb_ctx* c) {
   cudaFree(c->localbase);
   cudaFree(c->next_hist);
   cudaFree(c->next_hist_all);
+  cudaFree(c->scratch[0]);
+  cudaFree(c->scratch[1]);
+  cudaFree(c->dense_local);
+  cudaFree(c->dense_mine);
+  cudaFree(c->next_dense);
+  cudaFree(c->c_all);
+  cudaFree(c->mybase_v);
+  cudaFree(c->localbase_v);
+  cudaFree(c->bases_v);
+  cudaFree(c->seg_start_v);
+  cudaFree(c->seg_tiles_v);
+  for (int q = 0; q < 8; q++) {
+    if (c->ev_sorted[q]) cudaEventDestroy(c->ev_sorted[q]);
+    if (c->ev_xs[q]) cudaEventDestroy(c->ev_xs[q]);
+    if (c->ev_x[q]) cudaEventDestroy(c->ev_x[q]);
+  }
+  if (c->xstream) cudaStreamDestroy(c->xstream);
   cudaFree(c->seg_tile_start);
   cudaFree(c->one_seg_start);
   cudaFree(c->one_seg_tiles);
@@ -863,6 +1088,7 @@ int lsb_sort(lsb_ctx* c, lsb_stats* st) {
   CU(c, cudaSetDevice(c->cfg.device));
   if ((rc = begin_call(c))) return rc;
   c->hist_ready_digit = -1;
+  c->dense_ready_digit = -1;
   int subpasses = 0;
   if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) {
     if ((rc = passes_single(c, 0, c->npasses, &subpasses))) return rc;
@@ -879,6 +1105,8 @@ int lsb_pass(lsb_ctx* c, int digit, lsb_stats* st) {
   if (digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_pass: digit out of range");
   CU(c, cudaSetDevice(c->cfg.device));
   if ((rc = begin_call(c))) return rc;
+  c->hist_ready_digit = -1;
+  c->dense_ready_digit = -1;
   int subpasses = 0;
   if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) rc = passes_single(c, digit, digit + 1, &subpasses);
   else rc = pass_global(c, digit, &subpasses, false);

@@ -28,6 +28,7 @@ FLAG_PHASE_EVENTS = 1
 FLAG_TWO_LEVEL = 2
 FLAG_DIRECT_SCATTER = 4
 FLAG_NO_SKIP = 8
+FLAG_NO_PIPELINE = 16
 
 
 class LsbError(RuntimeError):

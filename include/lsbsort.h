@@ -88,6 +88,8 @@ typedef struct lsb_config {
                                     (a stable pass on a constant digit is the identity; the
                                     reference always runs it; chpl passes nBits for the same
                                     purpose, chpl/arkouda-radix-sort.chpl:70,78)              */
+#define LSB_FLAG_NO_PIPELINE 16u  /* G > 1: sort the whole shard, then exchange it (no overlap of the
+                                    NVLink time with the local sort of the next part)          */
 #define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (segment count + global scan +
                                     segmented scatter) even when world_size == 1            */
 
