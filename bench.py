@@ -223,11 +223,12 @@ def main_cuda(args, rank, world, local_rank):
         st = sorter.my_sort()
         kp_ms.append(st.partition_ms / max(st.partition_launches, 1))
         kp_n = st.partition_launches
+        kp_elems = st.partition_elements / max(st.partition_launches, 1)  # elements per launch (a part when pipelined)
         hist_ms.append(st.hist_ms)
     peak, peak_src = _peaks()
     here = sorter.here
     launch_ms = statistics.mean(kp_ms)
-    achieved = here * 32 / (launch_ms * 1e-3) / 1e9
+    achieved = kp_elems * 32 / (launch_ms * 1e-3) / 1e9
     npass = sorter.num_passes()
     sort_ms = statistics.mean(step_ms)
     # t_pass >= max(m*32 B / BW_hbm, m*16 B*f_remote / BW_nvlink); NVLink denominator =
@@ -241,7 +242,7 @@ def main_cuda(args, rank, world, local_rank):
     tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_element", 0) * here or None  # per launch of `here` elements
+            traffic = json.load(f).get("dram_bytes_per_element", 0) * kp_elems or None  # per launch
 
     # ---- end to end through the host-buffer C-ABI entry point ----
     # Every rank pins an input and an output buffer for its whole shard; if the host cannot hold
@@ -306,7 +307,7 @@ def main_cuda(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "lsb::partition_kernel (one 8-bit stable counting-sort step)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": here * 32, "launch_ms": launch_ms,
+                         "algorithmic_bytes_per_launch": kp_elems * 32, "launch_ms": launch_ms,
                          "launches_per_sort": kp_n,
                          "note": "a launch reads and writes every 16-byte element once (32 B/elem); a 16-bit "
                                  "reference pass takes two launches, see pass_roofline"},
@@ -354,7 +355,13 @@ def main():
         return subprocess.call(cmd)
     if args.impl == "reference":
         return main_reference(args, rank)
-    return main_cuda(args, rank, world, local_rank)
+    try:
+        return main_cuda(args, rank, world, local_rank)
+    except BaseException:  # a rank that dies quietly would leave its peers waiting in a collective
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

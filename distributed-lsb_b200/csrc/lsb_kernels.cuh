@@ -1091,32 +1091,34 @@ __global__ void dense_count32_kernel(const Elt* src, int64_t m, int shift, uint3
 }
 
 // global_scan_kernel for virtual ranks: counts[vr][d] (u32), scan in digit-major, virtual-rank-minor
-// order; mybase[q][d] for this GPU's V parts (vr = first_vr + q), sent[] summed over the parts
+// order; mybase[q][d] for this GPU's V parts (vr = first_vr + q), sent[] summed over the parts.
+// Three small launches so that every pass over the [GV][nb] table is coalesced and spread over many
+// CTAs: per-digit totals, exclusive scan of the totals (global_scan_kernel with G = 1), placement.
 struct VrScanArgs {
   const unsigned* counts;  // [GV][nb]
   int32_t nb, GV, first_vr, V, G;
   int64_t per;             // destination shard size
+  unsigned long long* totals;  // [nb] scratch: sum over virtual ranks
+  const int64_t* digit_base;   // [nb] exclusive scan of totals
   int64_t* mybase;         // [V][nb]
   unsigned long long* sent;  // [G], caller zeroes (may be null)
 };
 
-__global__ void __launch_bounds__(1024) vr_scan_kernel(const VrScanArgs a) {
-  __shared__ uint64_t wtot[32];
+__global__ void __launch_bounds__(256) vr_totals_kernel(const VrScanArgs a) {
+  const int d = blockIdx.x * 256 + threadIdx.x;
+  if (d >= a.nb) return;
+  unsigned long long t = 0;
+  for (int vr = 0; vr < a.GV; vr++) t += a.counts[(size_t)vr * a.nb + d];
+  a.totals[d] = t;
+}
+
+__global__ void __launch_bounds__(256) vr_place_kernel(const VrScanArgs a) {
   __shared__ unsigned long long s_sent[8];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  if (t < 8) s_sent[t] = 0;
-  const int chunk = (a.nb + 1023) / 1024;
-  const int d0 = t * chunk, d1 = min(d0 + chunk, a.nb);
-  uint64_t local = 0;
-  for (int vr = 0; vr < a.GV; vr++)
-    for (int d = d0; d < d1; d++) local += a.counts[(size_t)vr * a.nb + d];
-  const uint64_t incl = warp_incl_scan(local);
-  if (lane == 31) wtot[w] = incl;
+  if (threadIdx.x < 8) s_sent[threadIdx.x] = 0;
   __syncthreads();
-  uint64_t run = incl - local;
-  for (int i = 0; i < w; i++) run += wtot[i];
-  unsigned long long sent[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int d = d0; d < d1; d++)
+  const int d = blockIdx.x * 256 + threadIdx.x;
+  if (d < a.nb) {
+    uint64_t run = (uint64_t)a.digit_base[d];
     for (int vr = 0; vr < a.GV; vr++) {
       const uint64_t c = a.counts[(size_t)vr * a.nb + d];
       const int q = vr - a.first_vr;
@@ -1128,19 +1130,16 @@ __global__ void __launch_bounds__(1024) vr_scan_kernel(const VrScanArgs a) {
             const uint64_t r = b / (uint64_t)a.per;
             const uint64_t lim = (r + 1) * (uint64_t)a.per;
             const uint64_t x = e < lim ? e : lim;
-            sent[r] += x - b;
+            atomicAdd(&s_sent[r], (unsigned long long)(x - b));
             b = x;
           }
         }
       }
       run += c;
     }
-  if (a.sent) {
-    for (int g = 0; g < a.G; g++)
-      if (sent[g]) atomicAdd(&s_sent[g], sent[g]);
-    __syncthreads();
-    if (t < a.G) a.sent[t] = s_sent[t];
   }
+  __syncthreads();
+  if (a.sent && threadIdx.x < a.G && s_sent[threadIdx.x]) atomicAdd(a.sent + threadIdx.x, s_sent[threadIdx.x]);
 }
 
 // one block per part: where each digit's run starts inside the sorted part (localbase), and the

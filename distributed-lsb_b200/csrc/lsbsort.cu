@@ -102,6 +102,7 @@ struct lsb_ctx {
   std::vector<cudaEvent_t> phase_ev;
   std::vector<int> phase_kind;  // 0 hist, 1 scan/collective, 2 partition
   int64_t launches = 0;
+  int64_t part_elems = 0;
   int skipped = 0;
   unsigned long long* host_hist = nullptr;  // pinned [HIST_MAX_SUB][256]
   std::string err;
@@ -190,6 +191,7 @@ int begin_call(lsb_ctx* c) {
   c->phase_ev.clear();
   c->phase_kind.clear();
   c->launches = 0;
+  c->part_elems = 0;
   c->skipped = 0;
   c->next_counter = 0;
   CU(c, cudaMemsetAsync(c->tile_counters, 0, 256 * sizeof(uint32_t), c->stream));
@@ -228,6 +230,7 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
     }
   }
   st->partition_launches = subpasses;
+  st->partition_elements = c->part_elems;
   if (c->exchange_ms_acc > 0) st->exchange_ms = c->exchange_ms_acc;
   if (c->G > 1) {
     CU(c, cudaMemcpy(c->host_small, c->small, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -322,6 +325,7 @@ int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bi
   }
   const int64_t m_launch = m_override >= 0 ? m_override : c->here;
   const int64_t max_tiles = div_ceil(m_launch, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
+  c->part_elems += m_launch;
   if (m_launch > 0) {
     const bool runs = full_shift >= 0;
     if (runs) {
@@ -590,9 +594,22 @@ int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next)
     v.V = V;
     v.G = c->G;
     v.per = c->per;
+    v.totals = c->counts_local;                          // [nb] u64 scratch
+    v.digit_base = c->localbase;                         // [nb] i64 scratch
     v.mybase = c->mybase_v;
     v.sent = c->small;
-    vr_scan_kernel<<<1, 1024, 0, c->stream>>>(v);
+    vr_totals_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
+    GlobalScanArgs gs;
+    gs.counts = c->counts_local;
+    gs.nb = nb;
+    gs.G = 1;
+    gs.my = 0;
+    gs.per = INT64_MAX / 16;
+    gs.mybase = c->localbase;
+    gs.sent = nullptr;
+    global_scan_kernel<<<1, 1024, 0, c->stream>>>(gs);
+    vr_place_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
+    c->launches += 2;
     PartPrepArgs pp;
     pp.counts = c->c_all + (size_t)c->my * V * nb;
     pp.nb = nb;

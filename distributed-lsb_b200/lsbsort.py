@@ -48,7 +48,7 @@ class Stats(ctypes.Structure):
     _fields_ = [("device_ms", ctypes.c_double), ("passes", ctypes.c_int32), ("subpasses", ctypes.c_int32), ("skipped", ctypes.c_int32), ("reserved0", ctypes.c_int32),
                 ("elements", ctypes.c_int64), ("hist_ms", ctypes.c_double), ("scan_ms", ctypes.c_double),
                 ("partition_ms", ctypes.c_double), ("exchange_ms", ctypes.c_double), ("subpass_ms", ctypes.c_double * LSB_MAX_SUBPASSES),
-                ("sent", ctypes.c_int64 * LSB_MAX_GPUS), ("partition_launches", ctypes.c_int64),
+                ("sent", ctypes.c_int64 * LSB_MAX_GPUS), ("partition_launches", ctypes.c_int64), ("partition_elements", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_int64)]
 
 

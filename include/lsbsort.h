@@ -108,6 +108,7 @@ typedef struct lsb_stats {
   double subpass_ms[LSB_MAX_SUBPASSES]; /* per partition-kernel launch                     */
   int64_t sent[LSB_MAX_GPUS]; /* last pass: elements this shard sent to each GPU (:553-554) */
   int64_t partition_launches;
+  int64_t partition_elements; /* elements moved by all partition launches of the call          */
   int64_t kernel_launches; /* all kernels launched by the call                             */
 } lsb_stats;
 

@@ -267,7 +267,8 @@ def test_randomised_parity_sweep():
         bits = int(rng.choice([1, 3, 5, 7, 8, 9, 10, 11, 12, 14, 15, 16])) if case % 3 == 0 else 16
         mask = masks[int(rng.integers(0, len(masks)))]
         k = int(rng.integers(1, 4))
-        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_DIRECT_SCATTER][case % 4]
+        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_DIRECT_SCATTER,
+                 L.FLAG_TWO_LEVEL | L.FLAG_NO_PIPELINE][case % 5]
         if bits < 4 and n > 20000:
             n = 20000  # 64 passes of a 1-bit digit: keep the oracle quick
         g = O.generate(n, R, key_mask=mask, and_draws=k)
