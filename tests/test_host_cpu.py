@@ -101,3 +101,19 @@ def test_two_rank_gloo_counts_to_starts(bits):
         assert (res[r][2] == starts[:, r]).all()
         assert (res[r][3] == sc[r]).all()
         assert res[r][4] == float(world)
+
+
+@pytest.mark.parametrize("R,V", [(2, 4), (4, 4), (8, 2), (3, 5)])
+def test_virtual_ranks_do_not_change_the_pass(R, V):
+    """the pipelined multi-GPU pass treats part q of GPU g as rank g*V+q of the reference's algorithm:
+    refining the block distribution leaves every pass's output unchanged (it is a stable partition of
+    the global array), only the count tables get finer"""
+    n = R * V * 5000  # divisible, so the refined blocks are exactly the parts
+    a = O.generate(n, R)[:n]
+    for p in range(2):
+        coarse, counts_c, _, sc_c = O.one_pass(a, n, R, 16, p)
+        fine, counts_f, _, sc_f = O.one_pass(a, n, R * V, 16, p)
+        assert (coarse == fine).all()
+        assert (counts_f.reshape(R, V, -1).sum(axis=1) == counts_c).all()
+        assert (sc_f.reshape(R, V, R, V).sum(axis=(1, 3)) == sc_c).all()
+        a = coarse
