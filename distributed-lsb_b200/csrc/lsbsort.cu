@@ -6,11 +6,13 @@
 //
 //   G == 1 : [low sub-digit] A -> B, [high sub-digit] B -> A, both over the whole shard,
 //            with every 256-bin histogram of the whole sort taken in ONE up-front read.
-//   G  > 1 : [low sub-digit] local A -> B (shard becomes grouped by the low bits =
-//            "segments"), count of the full digit per segment, NCCL all-gather of the
-//            counts + digit-major/rank-minor exclusive scan (== :327-479), then
-//            [high sub-digit] B -> A where the destination is the GLOBAL output index and
-//            the store goes directly into the owning GPU's shard over NVLink (== :530-576).
+//   G  > 1 : the shard is cut into V parts (virtual ranks g*V+q).  Counts of the full digit per
+//            part are known before the pass starts (first pass: counted; later: produced by the
+//            previous pass's exchange kernel), NCCL reduce-scatter/all-gather + digit-major /
+//            rank-minor exclusive scan (== :327-479) give every part its global offsets, then per
+//            part: [low sub-digit] part -> scratch, [high sub-digit] scratch -> part (both local),
+//            and an exchange kernel that stores every run straight into the owning GPU's other
+//            shard over NVLink (== :530-576) while the next part is being sorted.
 //
 // Two stable steps (low bits, then high bits) are exactly one stable step on the full
 // digit, so the array after each pass is bit-identical to the reference's.
