@@ -25,4 +25,4 @@ with lsb.DistributedSorter(1 << a.log2n, ranks=1, radix_bits=a.radix, key_mask=a
         print(f"iter {i}: sort {st.device_ms:.3f} ms = {n / st.device_ms / 1e3:.1f} M elem/s; hist {st.hist_ms:.3f} ms "
               f"({n * 16 / st.hist_ms / 1e6:.0f} GB/s); partition {st.partition_ms / st.partition_launches:.3f} ms/launch "
               f"({n * 32 / (st.partition_ms / st.partition_launches) / 1e6:.0f} GB/s) x{st.partition_launches}; "
-              f"scan {st.scan_ms:.3f} ms; subpasses {[round(st.subpass_ms[k], 2) for k in range(st.subpasses)]}")
+              f"scan {st.scan_ms:.3f} ms; subpasses {[round(st.subpass_ms[k], 2) for k in range(min(st.subpasses, 32))]}")
