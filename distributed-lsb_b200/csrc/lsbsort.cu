@@ -847,8 +847,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
     const bool multi = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
     c->pipelined = multi && !(cfg->flags & (LSB_FLAG_NO_PIPELINE | LSB_FLAG_DIRECT_SCATTER));
     const char* v = getenv("LSB_VPARTS");
-    c->V = v ? atoi(v) : 4;
-    if (c->V < 1 || c->V > 8) c->V = 4;
+    c->V = v ? atoi(v) : 8;
+    if (c->V < 1 || c->V > 8) c->V = 8;
     c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
   }
   if (c->pipelined) {
