@@ -19,4 +19,5 @@ from .lsbsort import (  # noqa: F401
     header_symbols,
     library_path,
     load_library,
+    tune,
 )

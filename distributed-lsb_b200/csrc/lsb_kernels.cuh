@@ -2,10 +2,10 @@
 //
 // Reference path being replaced (citations relative to /root/reference/):
 //   generator loop ............ mpi/mpi_lsbsort.cpp:650-656   -> generate_kernel
-//   localShuffle count ........ mpi/mpi_lsbsort.cpp:226-229   -> hist_kernel / seg_count_kernel
+//   localShuffle count ........ mpi/mpi_lsbsort.cpp:226-229   -> digit_hist_kernel (lsb_onepass.cuh)
 //   count transpose + scan .... mpi/mpi_lsbsort.cpp:327-479   -> scan kernels (digit-major, rank-minor)
-//   localShuffle scatter,
-//   pack / alltoallv / unpack . mpi/mpi_lsbsort.cpp:241-246,530-576 -> partition_kernel
+//   localShuffle scatter ...... mpi/mpi_lsbsort.cpp:241-246   -> onepass_kernel (lsb_onepass.cuh), partition_kernel
+//   pack / alltoallv / unpack . mpi/mpi_lsbsort.cpp:530-576   -> exchange_vr_kernel
 //   verify .................... mpi/mpi_lsbsort.cpp:710-739   -> verify_kernel / checksum
 //
 // Everything here is integer/byte work bound by HBM (and NVLink for G > 1); no tensor cores.
@@ -145,150 +145,6 @@ __global__ void __launch_bounds__(GEN_THREADS) generate_kernel(const GenArgs a) 
 }
 
 // ------------------------------------------------------------------------------------
-// count kernels (localShuffle's count loop, mpi/mpi_lsbsort.cpp:226-229)
-// ------------------------------------------------------------------------------------
-constexpr int HIST_THREADS = 512;
-constexpr int HIST_MAX_SUB = 16;
-
-struct HistArgs {
-  const Elt* src;
-  int64_t m;
-  int32_t nsub;
-  int32_t shift[HIST_MAX_SUB];
-  uint32_t mask[HIST_MAX_SUB];
-  unsigned long long* out;  // [nsub][256], accumulated with atomics (caller zeroes)
-};
-
-// warp-aggregated shared-memory increment: when the whole warp hits one bin (the
-// skewed-key case: upper digits all zero) one lane adds the population count instead of
-// 32 serialised same-address atomics.
-__device__ __forceinline__ void smem_count(unsigned* hist, unsigned bin, unsigned active) {
-  int all_same;
-  __match_all_sync(active, bin, &all_same);
-  if (all_same) {
-    if ((threadIdx.x & 31) == (__ffs(active) - 1)) atomicAdd(hist + bin, __popc(active));
-  } else {
-    atomicAdd(hist + bin, 1u);
-  }
-}
-
-// One read of the shard produces the 256-bin histograms of up to 16 sub-digits (every
-// sub-pass of a single-GPU sort): block-private shared-memory histograms, coalesced
-// 8-byte key loads with 4 loads in flight per thread, one global atomic per bin per CTA.
-// NSUB is a compile-time count so the per-key loop is fully unrolled with shifts and masks
-// in registers; BYTES = the sub-digits are exactly bytes 0..NSUB-1 of the key (radix 8/16).
-// Skew: when the whole warp agrees on the key's upper 32 bits (keys with few random bits),
-// the sub-digits that live there are counted by one lane (+32) instead of a 32-way
-// same-address atomic.
-template <int NSUB, bool BYTES>
-__device__ __forceinline__ void hist_key(unsigned* sh, uint64_t k, const int* shift, const unsigned* mask,
-                                         unsigned active) {
-  const unsigned hi = (unsigned)(k >> 32);
-  const bool hi_uniform = __all_sync(active, hi == __shfl_sync(active, hi, __ffs(active) - 1));
-  const bool leader = (threadIdx.x & 31) == (__ffs(active) - 1);
-#pragma unroll
-  for (int s = 0; s < NSUB; s++) {
-    const int sh_s = BYTES ? 8 * s : shift[s];
-    const unsigned bin = BYTES ? (unsigned)(k >> (8 * s)) & 255u : (unsigned)(k >> sh_s) & mask[s];
-    const bool in_hi = BYTES ? (s >= 4) : (sh_s >= 32);
-    if (in_hi && hi_uniform) {
-      if (leader) atomicAdd(sh + s * 256 + bin, (unsigned)__popc(active));
-    } else {
-      atomicAdd(sh + s * 256 + bin, 1u);
-    }
-  }
-}
-
-template <int NSUB, bool BYTES>
-__global__ void __launch_bounds__(HIST_THREADS) hist_kernel(const HistArgs a) {
-  __shared__ unsigned sh[NSUB * 256];
-  for (int i = threadIdx.x; i < NSUB * 256; i += HIST_THREADS) sh[i] = 0;
-  int shift[NSUB];
-  unsigned mask[NSUB];
-#pragma unroll
-  for (int s = 0; s < NSUB; s++) { shift[s] = a.shift[s]; mask[s] = a.mask[s]; }
-  __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * HIST_THREADS;
-  int64_t i = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
-  constexpr int U = 4;
-  for (; i + (U - 1) * stride < a.m; i += U * stride) {
-    uint64_t k[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) k[u] = ld_stream_key(a.src + i + u * stride);
-#pragma unroll
-    for (int u = 0; u < U; u++) hist_key<NSUB, BYTES>(sh, k[u], shift, mask, 0xffffffffu);
-  }
-  for (; i < a.m; i += stride) {
-    const unsigned active = __activemask();
-    hist_key<NSUB, BYTES>(sh, ld_stream_key(a.src + i), shift, mask, active);
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < NSUB * 256; j += HIST_THREADS)
-    if (sh[j]) atomicAdd(a.out + j, (unsigned long long)sh[j]);
-}
-
-// Per-shard counts of a full (up to 16-bit) digit over a buffer that is already grouped
-// by the digit's low `lo_bits` (segment s = low bits, seg_start[s] .. seg_start[s+1]):
-// inside a segment only the high sub-digit varies, so a 256-bin shared histogram per
-// (CTA, segment piece) suffices.  out[(hi << lo_bits) | s].
-struct SegCountArgs {
-  const Elt* src;
-  int64_t m;
-  const int64_t* seg_start;  // [nseg + 1]
-  int32_t lo_bits;
-  int32_t shift_hi;
-  uint32_t mask_hi;
-  unsigned long long* out;   // [256 << lo_bits], caller zeroes
-};
-
-__global__ void __launch_bounds__(HIST_THREADS) seg_count_kernel(const SegCountArgs a) {
-  __shared__ unsigned sh[256];
-  __shared__ int s_seg_lo;
-  const int nseg = 1 << a.lo_bits;
-  // contiguous chunk of this CTA, multiple of HIST_THREADS elements
-  int64_t chunk = (a.m + gridDim.x - 1) / gridDim.x;
-  chunk = (chunk + HIST_THREADS - 1) / HIST_THREADS * HIST_THREADS;
-  const int64_t c0 = (int64_t)blockIdx.x * chunk;
-  const int64_t c1 = (c0 + chunk < a.m) ? c0 + chunk : a.m;
-  if (c0 >= c1) return;
-  if (threadIdx.x == 0) {  // last segment whose start is <= c0
-    int lo = 0, hi = nseg;
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (a.seg_start[mid] <= c0) lo = mid; else hi = mid;
-    }
-    s_seg_lo = lo;
-  }
-  if (threadIdx.x < 256) sh[threadIdx.x] = 0;
-  __syncthreads();
-  for (int seg = s_seg_lo; seg < nseg; seg++) {
-    const int64_t b = a.seg_start[seg] > c0 ? a.seg_start[seg] : c0;
-    const int64_t e = a.seg_start[seg + 1] < c1 ? a.seg_start[seg + 1] : c1;
-    if (a.seg_start[seg] >= c1) break;
-    if (b >= e) continue;
-    for (int64_t i = b + threadIdx.x; i < e; i += HIST_THREADS) {
-      unsigned active = __activemask();
-      uint64_t k = ld_stream_key(a.src + i);
-      smem_count(sh, (unsigned)(k >> a.shift_hi) & a.mask_hi, active);
-    }
-    __syncthreads();
-    if (threadIdx.x < 256) {
-      unsigned c = sh[threadIdx.x];
-      if (c) atomicAdd(a.out + (((size_t)threadIdx.x << a.lo_bits) | (unsigned)seg), (unsigned long long)c);
-      sh[threadIdx.x] = 0;
-    }
-    __syncthreads();
-  }
-}
-
-// test hook (lsb_histogram): dense count of a full digit in whatever order the shard is in
-__global__ void dense_count_kernel(const Elt* src, int64_t m, int shift, uint32_t mask, unsigned long long* out) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
-    atomicAdd(out + ((unsigned)(ld_stream_key(src + i) >> shift) & mask), 1ULL);
-}
-
-// ------------------------------------------------------------------------------------
 // scans
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
@@ -299,37 +155,6 @@ __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
     if (lane >= d) v += o;
   }
   return v;
-}
-
-// blockDim.x == 256: exclusive scan of one 256-bin histogram per block.
-// out[b*257 + 0..255] = exclusive prefix, out[b*257 + 256] = total.
-__global__ void __launch_bounds__(256) scan256_kernel(const unsigned long long* hist, int64_t* out) {
-  __shared__ uint64_t wtot[8];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const uint64_t c = hist[(size_t)blockIdx.x * 256 + t];
-  const uint64_t incl = warp_incl_scan(c);
-  if (lane == 31) wtot[w] = incl;
-  __syncthreads();
-  uint64_t off = 0;
-  for (int i = 0; i < w; i++) off += wtot[i];
-  out[(size_t)blockIdx.x * 257 + t] = (int64_t)(off + incl - c);
-  if (t == 255) out[(size_t)blockIdx.x * 257 + 256] = (int64_t)(off + incl);
-}
-
-// tiles per segment -> exclusive prefix (nseg <= 256, blockDim.x == 256)
-__global__ void __launch_bounds__(256) seg_tiles_kernel(const int64_t* seg_start, int nseg, int tile,
-                                                        uint32_t* seg_tile_start) {
-  __shared__ uint64_t wtot[8];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  uint64_t c = 0;
-  if (t < nseg) c = (uint64_t)((seg_start[t + 1] - seg_start[t] + tile - 1) / tile);
-  const uint64_t incl = warp_incl_scan(c);
-  if (lane == 31) wtot[w] = incl;
-  __syncthreads();
-  uint64_t off = 0;
-  for (int i = 0; i < w; i++) off += wtot[i];
-  if (t < nseg) seg_tile_start[t] = (uint32_t)(off + incl - c);
-  if (t == nseg - 1) seg_tile_start[nseg] = (uint32_t)(off + incl);
 }
 
 // The reference's copyCountsToGlobalCounts + exclusiveScan + copyStartsFromGlobalStarts
@@ -391,31 +216,11 @@ __global__ void __launch_bounds__(1024) global_scan_kernel(const GlobalScanArgs 
 }
 
 // ------------------------------------------------------------------------------------
-// partition kernel: one stable counting-sort step on a sub-digit of <= 8 bits.
-//
-// This is localShuffle's scatter (:241-246) and, for the last sub-digit of a pass, also
-// the pack / MPI_Alltoallv / unpack exchange (:530-576): the destination index is the
-// GLOBAL output index, and the 16-byte store goes straight into the destination GPU's
-// shard (peer pointer over NVLink) -- no 24-byte ShuffleBufSortElement, no staging.
-//
-// Shape (one CTA = one tile of TILE elements, taken in input order by a dynamic tile id):
-//   1. the tile is pulled into shared memory by ONE bulk async copy (cp.async.bulk, TMA
-//      engine, mbarrier completion): no registers hold elements, so several CTAs fit per SM
-//      and their load / rank / look-back / store phases overlap each other;
-//   2. early counts: per-warp 256-bin histograms (packed u16, shared atomics) -> tile totals
-//      are published for the decoupled look-back before the ranking starts;
-//   3. stable ranks: per 32-element row, peers = 8 ballots, running per-warp offsets in
-//      shared memory; the rank is written as a 2-byte permutation entry perm[slot] = index;
-//   4. decoupled look-back over 64-bit {tag, count} words gives each bin's offset among
-//      earlier tiles (the tag is a per-launch generation, so the words are never cleared);
-//   5. slot p of the tile gathers raw[perm[p]] from shared memory: consecutive threads write
-//      consecutive 16-byte slots of a bin's run in the destination shard.
-// The input may be split into segments (already grouped by the low sub-digit); a tile never
-// straddles a segment, look-back restarts at each segment, and bin bases are per segment.
+// tile machinery shared by partition_kernel (below) and onepass_kernel (lsb_onepass.cuh):
+// a tile of elements sits in shared memory (pulled in by the TMA engine: cp.async.bulk with
+// mbarrier completion, so no registers hold elements), is ranked stably by an 8-bit key
+// with warp ballots, and is written out through a 2-byte permutation perm[slot] = index.
 // ------------------------------------------------------------------------------------
-constexpr int PT_LB_WINDOW = 4;
-constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
-
 template <int THREADS_, int IPT_, int MINB_>
 struct PartCfg {
   static constexpr int THREADS = THREADS_;
@@ -431,29 +236,6 @@ struct PartCfg {
   static constexpr int SMEM = SMEM_BINDST + 256 * 8;
 };
 
-struct PartArgs {
-  const Elt* src;
-  int32_t shift;
-  uint32_t mask;
-  int32_t seg_bits;                // nseg = 1 << seg_bits
-  const int64_t* seg_start;        // [nseg + 1] element offsets into src
-  const uint32_t* seg_tile_start;  // [nseg + 1] tile-index prefix
-  const int64_t* bases;            // [(bin << seg_bits) | seg]: global output index of this shard's
-                                   // first element of (seg, bin)
-  uint64_t* lookback;              // [tiles][256]
-  uint32_t* tile_counter;
-  uint64_t tag_agg;                // (2*gen+1) << 56
-  uint64_t tag_inc;                // (2*gen+2) << 56
-  int64_t per;                     // destination shard size (global index / per = shard)
-  int32_t world;
-  Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
-  // RUNS kernels only: the input is already grouped by the low bits of a wider digit, so the
-  // sorted tile is ordered by that full digit; count its runs into run_counts[digit]
-  unsigned long long* run_counts;
-  int32_t full_shift;
-  uint32_t full_mask;
-};
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -463,16 +245,19 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+  unsigned ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "LSB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra LSB_DONE;\n\t"
-      "bra LSB_WAIT;\n\t"
-      "LSB_DONE:\n\t}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  while (!mbar_try(bar, parity)) {}
 }
 // global -> shared bulk copy on the TMA engine; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
@@ -482,12 +267,11 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, 
                : "memory");
 }
 
-// lanes of `vmask` whose 8-bit `bin` equals mine: 8 ballots (match.any measured ~10x slower:
-// its cost grows with the number of distinct values, and a row of 32 bins is mostly distinct)
+// lanes of `vmask` whose 8-bit `bin` equals mine: 8 ballots (hardware match.any, whole or per
+// nibble, measured 30-40 % slower: its cost grows with the number of distinct values in the
+// warp, and a row of 32 bins is mostly distinct)
 template <bool FULL>
 __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
-  // (hardware match.any, whole or per nibble, measured 30-40 % slower: its cost grows with the
-  // number of distinct values in the warp, and a row of 32 bins is mostly distinct)
   unsigned peers = vmask;
   if (FULL) {
 #pragma unroll
@@ -516,89 +300,191 @@ __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
   return peers;
 }
 
-template <class C, bool FULL, bool RUNS>
-__device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
-                                               unsigned* s_wtot, int tile, int seg, int count, bool first,
-                                               int first_tile) {
-  Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
-  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
-  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
-  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// How a tile of `count` elements is dealt to the warps: rows of 32 elements in contiguous blocks
+// (warp order == index order, which the stable per-warp offsets need), as evenly as the count
+// allows, so a partly filled tile keeps every warp busy.  Only the last row of a tile can be
+// partial; it belongs to one warp and is handled outside the unrolled loop over full rows.
+struct RowPlan {
+  int row0;      // first row of this warp
+  int nfull;     // full rows of this warp
+  int ptail;     // elements in this warp's partial row (0 = none); the row index is row0 + nfull
+};
+template <class C>
+__device__ __forceinline__ RowPlan row_plan(int count) {
+  const int warp = threadIdx.x >> 5;
+  const int full = count >> 5, tail = count & 31;
+  const int rows = full + (tail ? 1 : 0);
+  const int rpw = (rows + C::WARPS - 1) / C::WARPS;
+  RowPlan r;
+  r.row0 = warp * rpw;
+  const int mine = max(0, min(rpw, rows - r.row0));
+  r.nfull = max(0, min(mine, full - r.row0));
+  r.ptail = (mine > r.nfull) ? tail : 0;
+  return r;
+}
 
-  mbar_wait(s_bar, 0);
-
-  // ---- bins of my elements (warp-striped rows), early per-warp counts ----
-  const int idx0 = warp * (32 * C::IPT) + lane;
-  unsigned bins[C::IPT];
+// bins of my elements + per-warp 256-bin counts (packed u16, shared atomics)
+template <class C>
+__device__ __forceinline__ void op_count(const Elt* s_raw, const RowPlan& rp, int shift, unsigned mask,
+                                         unsigned short* s_whist, unsigned (&bins)[C::IPT], unsigned& bin_p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
+  const Elt* row = s_raw + rp.row0 * 32 + lane;
 #pragma unroll
   for (int j = 0; j < C::IPT; j++) {
-    const int idx = idx0 + j * 32;
     bins[j] = 0;
-    if (FULL || idx < count) {
-      const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
+    if (j < rp.nfull) {
+      const unsigned bin = (unsigned)(row[j * 32].key >> shift) & mask;
       bins[j] = bin;
       atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
     }
   }
-  __syncthreads();
+  bin_p = 0;
+  if (lane < rp.ptail) {
+    const unsigned bin = (unsigned)(row[rp.nfull * 32].key >> shift) & mask;
+    bin_p = bin;
+    atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
+  }
+}
 
-  // ---- per bin: tile total (published at once), exclusive over warps, start inside the tile ----
+// threads 0..255 only (bin = tid): tile total of the bin, its start inside the sorted tile, and
+// the per-warp running offsets written back over the per-warp counts.  Uses named barrier 1.
+template <class C>
+__device__ __forceinline__ void op_scan(unsigned short* s_whist, unsigned* s_wtot, unsigned& tile_count,
+                                        unsigned& binstart) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned wc[C::WARPS];
+  tile_count = 0;
+#pragma unroll
+  for (int w = 0; w < C::WARPS; w++) {
+    wc[w] = s_whist[w * 256 + tid];
+    tile_count += wc[w];
+  }
+  unsigned incl = tile_count;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  binstart = incl - tile_count;
+  for (int i = 0; i < warp; i++) binstart += s_wtot[i];
+  unsigned run = binstart;
+#pragma unroll
+  for (int w = 0; w < C::WARPS; w++) {
+    s_whist[w * 256 + tid] = (unsigned short)run;
+    run += wc[w];
+  }
+}
+
+// stable ranks: slot of each element inside the sorted tile, written as a permutation
+template <class C>
+__device__ __forceinline__ void op_rank(const RowPlan& rp, unsigned short* s_whist, unsigned short* s_perm,
+                                        const unsigned (&bins)[C::IPT], unsigned bin_p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned short* wh = s_whist + warp * 256;
+  const unsigned lt = lanemask_lt();
+  const int idx0 = rp.row0 * 32 + lane;
+#pragma unroll
+  for (int j = 0; j < C::IPT; j++) {
+    if (j < rp.nfull) {
+      const unsigned bin = bins[j];
+      const unsigned peers = match_bin<true>(0xffffffffu, bin);
+      const unsigned old = wh[bin];
+      __syncwarp();
+      if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+      __syncwarp();
+      s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + j * 32);
+    }
+  }
+  if (rp.ptail) {  // warp-uniform
+    const bool valid = lane < rp.ptail;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned peers = match_bin<false>(vmask, bin_p);
+      const unsigned old = wh[bin_p];
+      __syncwarp(vmask);
+      if ((peers & lt) == 0) wh[bin_p] = (unsigned short)(old + __popc(peers));
+      __syncwarp(vmask);
+      s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + rp.nfull * 32);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// partition kernel: one stable counting-sort step on a digit of <= 8 bits, HBM -> HBM
+// (localShuffle's scatter, mpi/mpi_lsbsort.cpp:241-246, for the narrow digits of a radix
+// sweep; wider digits go through onepass_kernel).  One CTA = one tile, taken in input order
+// by a dynamic tile id so that predecessors are always resident:
+//   1. bulk-load the tile; 2. early per-warp counts -> tile totals published for the decoupled
+//   look-back before the ranking starts; 3. stable ranks; 4. look-back over 64-bit {tag, count}
+//   words, 4 predecessor tiles per round trip (the tag is a per-launch generation, so the words
+//   are never cleared); 5. consecutive threads write consecutive slots of a bin's run.
+// ------------------------------------------------------------------------------------
+constexpr int PT_LB_WINDOW = 4;
+constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
+
+struct PartArgs {
+  const Elt* src;
+  int64_t m;
+  int32_t shift;
+  uint32_t mask;
+  const int64_t* bases;  // [256]: output index of the first element of each bin
+  uint64_t* lookback;    // [tiles][256]
+  uint32_t* tile_counter;
+  uint64_t tag_agg;      // (2*gen+1) << 56
+  uint64_t tag_inc;      // (2*gen+2) << 56
+  Elt* dst;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
+  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
+  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
+  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile;
+  __shared__ unsigned s_wtot[8];
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const int t = (int)atomicAdd(a.tile_counter, 1u);  // grid == number of tiles
+    s_tile = t;
+    const long long begin = (long long)t * C::TILE;
+    const long long left = a.m - begin;
+    const unsigned cnt = (unsigned)(left < C::TILE ? left : C::TILE);
+    mbar_expect_tx(&s_bar, cnt * 16u);
+    bulk_load(s_raw, a.src + begin, cnt * 16u, &s_bar);
+  }
+  for (int i = tid; i < C::WARPS * 128; i += C::THREADS) reinterpret_cast<unsigned*>(s_whist)[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  const long long left = a.m - (long long)tile * C::TILE;
+  const int count = (int)(left < C::TILE ? left : C::TILE);
+  const bool first = tile == 0;
+  mbar_wait(&s_bar, 0);
+
+  unsigned bins[C::IPT], bin_p;
+  const RowPlan rp = row_plan<C>(count);
+  op_count<C>(s_raw, rp, a.shift, a.mask, s_whist, bins, bin_p);
+  __syncthreads();
   unsigned tile_count = 0, binstart = 0;
   uint64_t* my_state = nullptr;
   if (tid < 256) {
+    op_scan<C>(s_whist, s_wtot, tile_count, binstart);
     my_state = a.lookback + (size_t)tile * 256 + tid;
-    unsigned wc[C::WARPS];
-#pragma unroll
-    for (int w = 0; w < C::WARPS; w++) {
-      wc[w] = s_whist[w * 256 + tid];
-      tile_count += wc[w];
-    }
     st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
-    unsigned incl = tile_count;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    if (lane == 31) s_wtot[warp] = incl;
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // only the 8 scanning warps
-    binstart = incl - tile_count;
-    for (int i = 0; i < warp; i++) binstart += s_wtot[i];
-    unsigned run = binstart;
-#pragma unroll
-    for (int w = 0; w < C::WARPS; w++) {
-      s_whist[w * 256 + tid] = (unsigned short)run;
-      run += wc[w];
-    }
   }
   __syncthreads();
+  op_rank<C>(rp, s_whist, s_perm, bins, bin_p);
 
-  // ---- stable ranks: slot of each element inside the tile, written as a permutation ----
-  {
-    unsigned short* wh = s_whist + warp * 256;
-    const unsigned lt = lanemask_lt();
-#pragma unroll
-    for (int j = 0; j < C::IPT; j++) {
-      const int idx = idx0 + j * 32;
-      const bool valid = FULL || idx < count;
-      const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
-      if (valid) {
-        const unsigned bin = bins[j];
-        const unsigned peers = match_bin<FULL>(vmask, bin);
-        const unsigned old = wh[bin];
-        __syncwarp(vmask);
-        if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
-        __syncwarp(vmask);
-        s_perm[old + __popc(peers & lt)] = (unsigned short)idx;
-      }
-    }
-  }
-
-  // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
-  // A window of PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles
-  // in flight the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
+  // decoupled look-back: exclusive prefix of this bin over earlier tiles.  A window of
+  // PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles in flight
+  // the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
   if (tid < 256) {
     uint64_t excl = 0;
     if (!first) {
@@ -609,7 +495,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
 #pragma unroll
         for (int i = 0; i < PT_LB_WINDOW; i++) {
           const int t = look - i;
-          v[i] = (t >= first_tile) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
+          v[i] = (t >= 0) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
         }
         int used = 0;
 #pragma unroll
@@ -625,356 +511,20 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       }
       st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
     }
-    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)binstart;
+    s_bindst[tid] = a.bases[tid] + (long long)excl - (long long)binstart;
   }
   __syncthreads();
 
-  // ---- write: consecutive threads -> consecutive slots of a bin's run ----
 #pragma unroll
   for (int k = 0; k < C::IPT; k++) {
     const int p = k * C::THREADS + tid;
-    const bool valid = FULL || p < count;
-    Elt el;
-    el.key = 0;
-    el.val = 0;
-    if (valid) {
-      el = s_raw[s_perm[p]];
+    if (p < count) {
+      const Elt el = s_raw[s_perm[p]];
       const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
-      const long long g = s_bindst[bin] + p;
-      Elt* out;
-      if (a.world == 1) {
-        out = a.dst[0] + g;
-      } else {
-        int r = 0;
-        for (int q = 1; q < a.world; q++) r += (g >= (long long)q * a.per);
-        out = a.dst[r] + (g - (long long)r * a.per);
-      }
-      st_elt(out, el);
-    }
-    if (RUNS) {
-      // localShuffle's counts of the FULL digit (:226-229) as a by-product: the sorted tile is
-      // non-decreasing in the full digit, so each warp adds the length of every run it sees
-      const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
-      const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
-      const bool head = valid && (lane == 0 || d != prev);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      const unsigned nvalid = FULL ? 32u : (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
-      if (head) {
-        const unsigned after = heads & ~((2u << lane) - 1u);
-        const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
-        atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
-      }
+      st_elt(a.dst + (s_bindst[bin] + p), el);
     }
   }
 }
-
-template <class C, bool RUNS>
-__global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tile, s_seg, s_count, s_first, s_first_tile;
-  __shared__ unsigned s_wtot[8];
-
-  const int tid = threadIdx.x;
-  const int nseg = 1 << a.seg_bits;
-
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    const unsigned t = atomicAdd(a.tile_counter, 1u);
-    s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
-    s_seg = 0;
-  }
-  // zero the packed per-warp histograms (WARPS*256 u16)
-  for (int i = tid; i < C::WARPS * 128; i += C::THREADS)
-    reinterpret_cast<unsigned*>(smem + C::SMEM_WHIST)[i] = 0;
-  __syncthreads();
-  const int tile = s_tile;
-  if (tile < 0) return;
-  // which segment owns this tile: the one with first_tile <= tile < next first_tile
-  if (nseg > 1) {
-    if (tid < nseg) {
-      const unsigned f = a.seg_tile_start[tid], l = a.seg_tile_start[tid + 1];
-      if (f <= (unsigned)tile && (unsigned)tile < l) s_seg = tid;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    const int sg = s_seg;
-    const unsigned t_in = (unsigned)tile - a.seg_tile_start[sg];
-    const long long begin = a.seg_start[sg] + (long long)t_in * C::TILE;
-    const long long left = a.seg_start[sg + 1] - begin;
-    const int cnt = (int)(left < C::TILE ? left : C::TILE);
-    s_count = cnt;
-    s_first = (t_in == 0);
-    s_first_tile = (int)a.seg_tile_start[sg];
-    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
-    bulk_load(smem + C::SMEM_RAW, a.src + begin, (unsigned)cnt * 16u, &s_bar);
-  }
-  __syncthreads();
-  const int count = s_count;
-  if (count == C::TILE)
-    partition_tile<C, true, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
-  else
-    partition_tile<C, false, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
-}
-
-// tile shapes: {threads, elements per thread, CTAs per SM}; all need nseg <= THREADS
-typedef PartCfg<256, 8, 5> PartCfgA;   // 2048-element tiles, 43 KiB, 40 warps/SM
-typedef PartCfg<256, 15, 3> PartCfgB;  // 3840-element tiles, 74 KiB, 24 warps/SM
-typedef PartCfg<256, 11, 4> PartCfgC;  // 2816-element tiles, 56 KiB, 32 warps/SM
-typedef PartCfg<512, 10, 2> PartCfgD;  // 5120-element tiles, 100 KiB, 32 warps/SM
-typedef PartCfg<512, 11, 2> PartCfgE;  // 5632-element tiles, 109 KiB, 32 warps/SM
-typedef PartCfg<256, 22, 2> PartCfgF;  // 5632-element tiles, 105 KiB, 16 warps/SM
-
-// ------------------------------------------------------------------------------------
-// persistent partition kernel (single-segment inputs: every step except the direct-scatter
-// variant).  Same algorithm as partition_kernel, different execution shape:
-//   * one CTA of 1024 threads per SM loops over tiles (dynamic tile ids); the NEXT tile is
-//     pulled into the other half of a double-buffered shared-memory stage by a bulk async
-//     copy while the current one is being processed, so the HBM->SMEM latency is hidden;
-//   * 24 worker warps count / rank / write; 8 specialist warps (one thread per bin) own the
-//     per-bin bookkeeping: column sums, publishing the tile aggregate, and the decoupled
-//     look-back -- which now runs CONCURRENTLY with the workers' ranking instead of after it.
-// ------------------------------------------------------------------------------------
-template <int IPT_>
-struct PersistCfg {
-  static constexpr int THREADS = 1024;
-  static constexpr int WORK_WARPS = 24;
-  static constexpr int WORK_THREADS = WORK_WARPS * 32;  // 768; specialists are threads 768..1023
-  static constexpr int IPT = IPT_;                      // rows of 32 elements per worker warp
-  static constexpr int TILE = WORK_WARPS * 32 * IPT_;
-  static constexpr int SLOTS = (TILE + THREADS - 1) / THREADS;
-  static constexpr int SMEM_RAW0 = 0;
-  static constexpr int SMEM_RAW1 = TILE * 16;
-  static constexpr int SMEM_PERM = 2 * TILE * 16;
-  static constexpr int SMEM_WHIST = SMEM_PERM + ((TILE * 2 + 15) / 16) * 16;
-  static constexpr int SMEM_BINDST = SMEM_WHIST + WORK_WARPS * 256 * 2;
-  static constexpr int SMEM = SMEM_BINDST + 256 * 8;
-};
-
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-struct TileDesc {
-  int tile;   // -1: no more work
-  int count;
-};
-
-#ifndef PS_LB_WINDOW
-#define PS_LB_WINDOW 4
-#endif
-template <class C, bool RUNS>
-__global__ void __launch_bounds__(C::THREADS, 1) partition_persistent_kernel(const PartArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
-  unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
-  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
-  __shared__ __align__(8) uint64_t s_bar[2];
-  __shared__ TileDesc s_desc[2];
-  __shared__ unsigned s_wtot[8];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool worker = tid < C::WORK_THREADS;
-  const int64_t m = a.seg_start[1];                 // single segment: [0, m)
-  const unsigned total_tiles = a.seg_tile_start[1];
-
-  // start the bulk load of tile `t` into stage `b` (one thread)
-  auto prefetch = [&](int b, unsigned t) {
-    if (t < total_tiles) {
-      const long long begin = (long long)t * C::TILE;
-      const long long left = m - begin;
-      const int cnt = (int)(left < C::TILE ? left : C::TILE);
-      s_desc[b].tile = (int)t;
-      s_desc[b].count = cnt;
-      mbar_expect_tx(&s_bar[b], (unsigned)cnt * 16u);
-      bulk_load(smem + (b ? C::SMEM_RAW1 : C::SMEM_RAW0), a.src + begin, (unsigned)cnt * 16u, &s_bar[b]);
-    } else {
-      s_desc[b].tile = -1;
-      s_desc[b].count = 0;
-    }
-  };
-
-  // tile ids come from an atomic counter; the scheduler thread keeps one id in flight so that the
-  // atomic's round trip never sits in front of a barrier
-  unsigned next_id = 0;
-  if (tid == C::THREADS - 1) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    prefetch(0, atomicAdd(a.tile_counter, 1u));
-    next_id = atomicAdd(a.tile_counter, 1u);
-  }
-  __syncthreads();
-
-  for (int it = 0;; it++) {
-    const int b = it & 1;
-    const int tile = s_desc[b].tile;
-    if (tile < 0) break;
-    const int count = s_desc[b].count;
-    const bool full = (count == C::TILE);
-    const bool first = (tile == 0);
-    Elt* s_raw = reinterpret_cast<Elt*>(smem + (b ? C::SMEM_RAW1 : C::SMEM_RAW0));
-    if (tid == C::THREADS - 1) {  // stage b^1 was released by the barrier that ended the last iteration
-      prefetch(b ^ 1, next_id);
-      if (next_id < total_tiles) next_id = atomicAdd(a.tile_counter, 1u);
-    }
-
-    // ---- workers: early per-warp counts ----
-    const int idx0 = warp * (32 * C::IPT) + lane;
-    unsigned bins[C::IPT];
-    if (worker) {
-      reinterpret_cast<uint4*>(s_whist + warp * 256)[lane] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-      while (!mbar_try(&s_bar[b], (unsigned)(it >> 1) & 1u)) {}
-      unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
-#pragma unroll
-      for (int j = 0; j < C::IPT; j++) {
-        const int idx = idx0 + j * 32;
-        bins[j] = 0;
-        if (full || idx < count) {
-          const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
-          bins[j] = bin;
-          atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
-        }
-      }
-    }
-    __syncthreads();  // A
-
-    // ---- specialists: per-bin totals, publish, bin starts, warp offsets ----
-    unsigned tile_count = 0, binstart = 0;
-    uint64_t* my_state = nullptr;
-    const int bin_t = tid - C::WORK_THREADS;  // 0..255 for specialists
-    if (!worker) {
-      my_state = a.lookback + (size_t)tile * 256 + bin_t;
-      unsigned wc[C::WORK_WARPS];
-#pragma unroll
-      for (int w = 0; w < C::WORK_WARPS; w++) {
-        wc[w] = s_whist[w * 256 + bin_t];
-        tile_count += wc[w];
-      }
-      st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
-      unsigned incl = tile_count;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += o;
-      }
-      const int sw = bin_t >> 5;
-      if (lane == 31) s_wtot[sw] = incl;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 specialist warps only
-      binstart = incl - tile_count;
-      for (int i = 0; i < sw; i++) binstart += s_wtot[i];
-      unsigned run = binstart;
-#pragma unroll
-      for (int w = 0; w < C::WORK_WARPS; w++) {
-        s_whist[w * 256 + bin_t] = (unsigned short)run;
-        run += wc[w];
-      }
-    }
-    __syncthreads();  // B
-
-    if (worker) {
-      // ---- stable ranks -> permutation ----
-      unsigned short* wh = s_whist + warp * 256;
-      const unsigned lt = lanemask_lt();
-      if (full) {
-#pragma unroll
-        for (int j = 0; j < C::IPT; j++) {
-          const unsigned bin = bins[j];
-          const unsigned peers = match_bin<true>(0xffffffffu, bin);
-          const unsigned old = wh[bin];
-          __syncwarp();
-          if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
-          __syncwarp();
-          s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + j * 32);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < C::IPT; j++) {
-          const int idx = idx0 + j * 32;
-          const bool valid = idx < count;
-          const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-          if (valid) {
-            const unsigned bin = bins[j];
-            const unsigned peers = match_bin<false>(vmask, bin);
-            const unsigned old = wh[bin];
-            __syncwarp(vmask);
-            if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
-            __syncwarp(vmask);
-            s_perm[old + __popc(peers & lt)] = (unsigned short)idx;
-          }
-        }
-      }
-    } else {
-      // ---- decoupled look-back, concurrent with the ranking ----
-      uint64_t excl = 0;
-      if (!first) {
-        int look = tile - 1;
-        bool done = false;
-        while (!done) {
-          uint64_t v[PS_LB_WINDOW];
-#pragma unroll
-          for (int i = 0; i < PS_LB_WINDOW; i++) {
-            const int t = look - i;
-            v[i] = (t >= 0) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + bin_t) : 0;
-          }
-          int used = 0;
-#pragma unroll
-          for (int i = 0; i < PS_LB_WINDOW; i++) {
-            if (!done && used == i) {
-              const uint64_t tag = v[i] & ~LB_VALUE_MASK;
-              if (tag == a.tag_inc) { excl += v[i] & LB_VALUE_MASK; done = true; }
-              else if (tag == a.tag_agg) { excl += v[i] & LB_VALUE_MASK; used = i + 1; }
-            }
-          }
-          look -= used;
-          if (!done && used == 0) __nanosleep(20);
-        }
-        st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
-      }
-      s_bindst[bin_t] = a.bases[bin_t] + (long long)excl - (long long)binstart;
-    }
-    __syncthreads();  // C
-
-    // ---- write: consecutive threads -> consecutive slots of a bin's run ----
-#pragma unroll
-    for (int k = 0; k < C::SLOTS; k++) {
-      const int p = k * C::THREADS + tid;
-      const bool valid = p < count;
-      Elt el;
-      el.key = 0;
-      el.val = 0;
-      if (valid) {
-        el = s_raw[s_perm[p]];
-        const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
-        st_elt(a.dst[0] + (s_bindst[bin] + p), el);
-      }
-      if (RUNS) {
-        const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
-        const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
-        const bool head = valid && (lane == 0 || d != prev);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const unsigned nvalid = (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
-        if (head) {
-          const unsigned after = heads & ~((2u << lane) - 1u);
-          const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
-          atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
-        }
-      }
-    }
-    __syncthreads();  // D: stage b and perm are free again
-  }
-}
-
-typedef PersistCfg<7> PersistCfgA;  // 5376-element tiles, 2 x 84 KiB stages, 195 KiB
 
 // ------------------------------------------------------------------------------------
 // exchange kernel (G > 1): the pack / MPI_Alltoallv / unpack of mpi/mpi_lsbsort.cpp:530-576
@@ -995,84 +545,6 @@ typedef PersistCfg<7> PersistCfgA;  // 5376-element tiles, 2 x 84 KiB stages, 19
 constexpr int EX_THREADS = LSB_EX_THREADS;
 constexpr int EX_U = LSB_EX_U;
 
-struct ExchArgs {
-  const Elt* src;
-  int64_t m;
-  int32_t shift;
-  uint32_t mask;
-  const int64_t* localbase;  // [nb] first local index of digit d in src
-  const int64_t* mybase;     // [nb] global output index of this shard's first element of digit d
-  int64_t per;
-  int32_t world;
-  Elt* dst[8];
-  // optional: while the elements stream by, count the sub-digits of the NEXT pass per destination
-  // GPU (the receiver sums the G contributions), so the next pass needs no count read of its own
-  int32_t next_nsub;              // 0 = off
-  int32_t next_shift[2];
-  uint32_t next_mask[2];
-  unsigned long long* next_hist;  // [G][2][256], caller zeroes
-};
-
-__global__ void __launch_bounds__(EX_THREADS) exchange_kernel(const ExchArgs a) {
-  __shared__ unsigned s_next[8 * 2 * 256];
-  if (a.next_nsub)
-    for (int i = threadIdx.x; i < a.world * 2 * 256; i += EX_THREADS) s_next[i] = 0;
-  // The shard is sorted by digit, so positions [k*m/G, (k+1)*m/G) go (roughly) to GPU k.  Chunks are
-  // dealt round-robin over those G parts so that at any moment the resident CTAs store to all G
-  // destinations at once: the local part (HBM-bound) overlaps the remote parts (NVLink-bound).
-  __shared__ Elt* s_dst[8];  // (indexing the kernel parameter dynamically would spill it to local memory)
-  __shared__ long long s_lim[8];
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      s_dst[q] = a.dst[q];
-      s_lim[q] = (long long)q * a.per;
-    }
-  }
-  __syncthreads();
-  const int64_t chunk = (int64_t)EX_THREADS * EX_U;
-  const int64_t part = ((a.m + a.world - 1) / a.world + chunk - 1) / chunk * chunk;  // multiple of chunk
-  const int64_t chunks_per_part = part / chunk;
-  const int64_t total = chunks_per_part * a.world;
-  for (int64_t k = blockIdx.x; k < total; k += gridDim.x) {
-    const int64_t c0 = (k % a.world) * part + (k / a.world) * chunk;
-    if (c0 >= a.m) continue;
-    Elt e[EX_U];
-#pragma unroll
-    for (int u = 0; u < EX_U; u++) {
-      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
-      if (i < a.m) e[u] = ld_stream(a.src + i);
-    }
-#pragma unroll
-    for (int u = 0; u < EX_U; u++) {
-      const int64_t i = c0 + u * EX_THREADS + threadIdx.x;
-      if (i < a.m) {
-        const unsigned d = (unsigned)(e[u].key >> a.shift) & a.mask;
-        const long long g = __ldg(a.mybase + d) + (i - __ldg(a.localbase + d));
-        int r = 0;
-        for (int q = 1; q < a.world; q++) r += (g >= s_lim[q]);
-        st_elt(s_dst[r] + (g - s_lim[r]), e[u]);
-        for (int s = 0; s < a.next_nsub; s++)
-          atomicAdd(&s_next[(r * 2 + s) * 256 + ((unsigned)(e[u].key >> a.next_shift[s]) & a.next_mask[s])], 1u);
-      }
-    }
-  }
-  if (a.next_nsub) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < a.world * 2 * 256; i += EX_THREADS)
-      if (s_next[i]) atomicAdd(a.next_hist + i, (unsigned long long)s_next[i]);
-  }
-}
-
-// hist[s][bin] = sum over source GPUs of next_hist_all[src][my][s][bin]  (blockDim = 512, one block)
-__global__ void __launch_bounds__(512) next_hist_reduce_kernel(const unsigned long long* all, int G, int my,
-                                                              unsigned long long* hist) {
-  const int i = threadIdx.x;  // (s, bin)
-  unsigned long long acc = 0;
-  for (int src = 0; src < G; src++) acc += all[((size_t)src * G + my) * 512 + i];
-  hist[i] = acc;
-}
-
 // ------------------------------------------------------------------------------------
 // Pipelined multi-GPU pass ("virtual ranks"): every shard is cut into V contiguous parts and
 // part q of GPU g acts as rank g*V+q of the reference's algorithm (its order is the global
@@ -1082,13 +554,6 @@ __global__ void __launch_bounds__(512) next_hist_reduce_kernel(const unsigned lo
 // pass p+1 are produced by the exchange kernel of pass p (one L2 atomic per element, hidden
 // under the NVLink time), per destination GPU and destination part.
 // ------------------------------------------------------------------------------------
-
-// counts[d] += 1 for a range (first pass only: nothing has counted this digit yet)
-__global__ void dense_count32_kernel(const Elt* src, int64_t m, int shift, uint32_t mask, unsigned* out) {
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride)
-    atomicAdd(out + ((unsigned)(ld_stream_key(src + i) >> shift) & mask), 1u);
-}
 
 // global_scan_kernel for virtual ranks: counts[vr][d] (u32), scan in digit-major, virtual-rank-minor
 // order; mybase[q][d] for this GPU's V parts (vr = first_vr + q), sent[] summed over the parts.
@@ -1145,7 +610,8 @@ __global__ void __launch_bounds__(256) vr_place_kernel(const VrScanArgs a) {
 // one block per part: where each digit's run starts inside the sorted part (localbase), and the
 // bases of the two local counting-sort steps (sub-digit histograms folded out of the dense counts)
 struct PartPrepArgs {
-  const unsigned* counts;  // [V][nb] this GPU's parts
+  const unsigned* counts;  // [V][nb] this GPU's parts, or
+  const unsigned long long* counts64;  // [nb] (one part: the whole shard) when counts == nullptr
   int32_t nb, lo_bits, hi_bits;
   int64_t* localbase;      // [V][nb]
   int64_t* bases;          // [V][2][257]: exclusive scans of the low / high sub-digit counts (+ total)
@@ -1155,7 +621,8 @@ __global__ void __launch_bounds__(1024) part_prep_kernel(const PartPrepArgs a) {
   __shared__ uint64_t wtot[32];
   __shared__ unsigned long long s_lo[256], s_hi[256];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const unsigned* c = a.counts + (size_t)blockIdx.x * a.nb;
+  const unsigned* c32 = a.counts ? a.counts + (size_t)blockIdx.x * a.nb : nullptr;
+  auto cnt = [&](int d) -> unsigned long long { return c32 ? (unsigned long long)c32[d] : a.counts64[d]; };
   int64_t* lb = a.localbase + (size_t)blockIdx.x * a.nb;
   if (t < 256) { s_lo[t] = 0; s_hi[t] = 0; }
   __syncthreads();
@@ -1164,11 +631,11 @@ __global__ void __launch_bounds__(1024) part_prep_kernel(const PartPrepArgs a) {
   const unsigned lo_mask = (1u << a.lo_bits) - 1;
   uint64_t local = 0;
   for (int d = d0; d < d1; d++) {
-    const unsigned v = c[d];
+    const unsigned long long v = cnt(d);
     local += v;
     if (v) {
-      if (a.lo_bits) atomicAdd(&s_lo[d & lo_mask], (unsigned long long)v);
-      atomicAdd(&s_hi[d >> a.lo_bits], (unsigned long long)v);
+      if (a.lo_bits) atomicAdd(&s_lo[d & lo_mask], v);
+      atomicAdd(&s_hi[d >> a.lo_bits], v);
     }
   }
   const uint64_t incl = warp_incl_scan(local);
@@ -1178,7 +645,7 @@ __global__ void __launch_bounds__(1024) part_prep_kernel(const PartPrepArgs a) {
   for (int i = 0; i < w; i++) run += wtot[i];
   for (int d = d0; d < d1; d++) {
     lb[d] = (int64_t)run;
-    run += c[d];
+    run += cnt(d);
   }
   __syncthreads();
   // exclusive scans of the two 256-bin histograms by warps 0 and 1 (8 bins per lane)

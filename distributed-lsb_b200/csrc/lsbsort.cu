@@ -1,23 +1,26 @@
-// lsbsort.cu -- C ABI (include/lsbsort.h) over the sm_100a kernels in lsb_kernels.cuh.
+// lsbsort.cu -- C ABI (include/lsbsort.h) over the sm_100a kernels in lsb_kernels.cuh /
+// lsb_onepass.cuh.
 //
 // Host-side restatement of the reference's pass structure, mpi/mpi_lsbsort.cpp:481-585
-// (globalShuffle / mySort), for device-resident shards.  A reference pass on a digit of
-// up to 16 bits is executed as one or two stable 8-bit counting-sort steps:
+// (globalShuffle / mySort), for device-resident shards.
 //
-//   G == 1 : [low sub-digit] A -> B, [high sub-digit] B -> A, both over the whole shard,
-//            with every 256-bin histogram of the whole sort taken in ONE up-front read.
+//   G == 1 : ONE read of the shard counts the digits of every pass (digit_hist_kernel); each pass
+//            is then one launch that moves every element through HBM once: onepass_kernel for
+//            digits of 9..16 bits (the reference's 16), partition_kernel for digits of <= 8 bits.
 //   G  > 1 : the shard is cut into V parts (virtual ranks g*V+q).  Counts of the full digit per
 //            part are known before the pass starts (first pass: counted; later: produced by the
 //            previous pass's exchange kernel), NCCL reduce-scatter/all-gather + digit-major /
 //            rank-minor exclusive scan (== :327-479) give every part its global offsets, then per
-//            part: [low sub-digit] part -> scratch, [high sub-digit] scratch -> part (both local),
-//            and an exchange kernel that stores every run straight into the owning GPU's other
-//            shard over NVLink (== :530-576) while the next part is being sorted.
+//            part: one local stable sort by the digit (same kernels as G == 1, == localShuffle,
+//            :213-247) into a scratch, and an exchange kernel that stores every run straight into
+//            the owning GPU's other shard over NVLink (== :530-576) while the next part is being
+//            sorted.
 //
-// Two stable steps (low bits, then high bits) are exactly one stable step on the full
-// digit, so the array after each pass is bit-identical to the reference's.
+// LSB_FLAG_TWO_STEP keeps round 1's shape for comparison: a 9..16-bit digit as two stable
+// 8-bit counting-sort steps over HBM (low bits, then high bits) -- the same permutation.
 #include "../../include/lsbsort.h"
 #include "lsb_kernels.cuh"
+#include "lsb_onepass.cuh"
 
 #include <nccl.h>  // types only: the library itself is bound at run time, see NcclApi
 #include <dlfcn.h>
@@ -33,6 +36,9 @@ using namespace lsb;
 
 namespace {
 
+typedef PartCfg<512, 11, 2> TileCfg;   // 5632-element tiles, 109 KiB, 2 CTAs (32 warps) per SM
+typedef PartCfg<256, 11, 4> TileCfgS;  // 2816-element tiles, 56 KiB, 4 CTAs (32 warps) per SM
+
 struct SubPass {
   int shift;
   int bits;
@@ -45,10 +51,26 @@ struct PassPlan {
   int hi_bits;
 };
 
+// process-wide tunables read by lsb_create (lsb_tune); defaults are what bench.py measures
+struct Tuning {
+  int op_cfg = 0;        // one-pass tile shape: 0 = 512 threads x 11 (2 CTAs/SM), 1 = 256 x 11 (4 CTAs/SM)
+  int op_persist = 0;    // MiB of L2 set aside for persisting (evict_last) lines, 0 = leave the device default
+  int op_t1 = 238;       // K1 tiles per supertile of the one-pass kernel (<= 256)
+  int op_nx = 3;         // supertile scratch buffers
+  int op_lead = 1;       // K1 phases claimed ahead of the matching K2 phase
+  int op_hints = 7;      // L2 eviction hints, see OnePassArgs::hints
+  int op_ctas_mgpu = 1;  // one-pass CTAs per SM while an exchange kernel shares the GPU (G > 1)
+  int vparts = 8;        // parts per shard of the multi-GPU pass
+  int ex_ctas = 1;       // exchange CTAs per SM
+  int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
+};
+Tuning g_tune;
+
 }  // namespace
 
 struct lsb_ctx {
   lsb_config cfg;
+  Tuning tune;
   int G = 1, my = 0;
   int64_t n = 0, per = 0, here = 0, first = 0, per_stream = 0;
   int npasses = 0;
@@ -57,44 +79,51 @@ struct lsb_ctx {
   int cur = 0;                        // which of buf[] holds the data
   Elt* peer[2][LSB_MAX_GPUS] = {};    // peer[b][g]: shard b of GPU g (own pointer for g == my)
   bool peer_open[2][LSB_MAX_GPUS] = {};
+  int num_sms = 0;
+  int tile = TileCfg::TILE;           // elements per tile of partition_kernel
+  int op_tile = TileCfg::TILE;        // elements per tile of onepass_kernel
+  // partition_kernel (digits of <= 8 bits, and LSB_FLAG_TWO_STEP)
   uint64_t* lookback = nullptr;
   size_t lookback_tiles = 0;
-  uint32_t* tile_counters = nullptr;  // [64]
+  uint32_t* tile_counters = nullptr;  // [TILE_COUNTERS], recycled
   int next_counter = 0;
   int gen = 0;
-  int variant = 0;   // partition tile shape (PartCfgA..F, 6 = persistent kernel), LSB_PT_VARIANT
-  int num_sms = 148;
-  int tile = 0;      // elements per partition tile
-  unsigned long long* hist = nullptr;        // [HIST_MAX_SUB][256]
-  int64_t* scan_out = nullptr;               // [HIST_MAX_SUB][257]
-  unsigned long long* counts_local = nullptr;  // [65536]
-  unsigned long long* counts_all = nullptr;    // [G][65536]
-  int64_t* mybase = nullptr;                 // [65536]
-  int64_t* localbase = nullptr;              // [65536]
-  unsigned long long* next_hist = nullptr;     // [G][2][256] counted by the exchange kernel
-  unsigned long long* next_hist_all = nullptr; // [G][G][2][256]
-  int hist_ready_digit = -1;                 // digit whose sub-digit histograms already sit in hist[]
+  // digit counts of a whole sort (G == 1) / of one pass
+  unsigned long long* hist16 = nullptr;  // [<= 4 * 65536] counts of every pass's digit, compact
+  int64_t* starts16 = nullptr;           // their exclusive scans (natural digit order)
+  int* dig_meta = nullptr;               // [2][64] device: offset / bins per pass
+  int* skip_flags = nullptr;             // [64] device
+  int* host_skip = nullptr;              // [64] pinned
+  unsigned long long* counts_all = nullptr;    // [G][65536] (lsb_starts without virtual ranks)
+  int64_t* mybase = nullptr;                   // [65536]
+  // one-pass kernel
+  int64_t op_S = 0;                   // elements per supertile
+  Elt* op_X = nullptr;                // [NX][S] supertile scratch (stays in L2)
+  unsigned* op_oc = nullptr;          // [NX][256][T1]
+  unsigned char* op_ctl = nullptr;    // control block + look-back ring, zeroed before every launch
+  size_t op_ctl_bytes = 0;
+  uint64_t* op_F = nullptr;           // [65536] frontier table
+  unsigned* op_err = nullptr;         // watchdog word, zeroed per call
+  unsigned long long* op_prof = nullptr;  // stage clocks of LSB_OP_PROF builds
+  int op_resident = 0;                // CTAs per SM the kernel can keep resident
   // pipelined pass (virtual ranks): shard cut into V parts
-  bool pipelined = false;
-  int V = 4;
+  bool two_level = false;
+  int V = 8;
   int64_t vpart = 0;                         // elements per part
-  Elt* scratch[2] = {nullptr, nullptr};      // part-sized scratch for the local sort of one part
+  Elt* scratch[2] = {nullptr, nullptr};      // part-sized scratch: the sorted part until it is exchanged
   unsigned* dense_local = nullptr;           // [V][65536] counts of the full digit per part (first pass)
   unsigned* next_dense = nullptr;            // [G][V][65536] counted by the exchange kernel for the next pass
   unsigned* dense_mine = nullptr;            // [V][65536] after the reduce-scatter
   unsigned* c_all = nullptr;                 // [G*V][65536] counts of every virtual rank
+  unsigned long long* totals = nullptr;      // [65536] scratch of the virtual-rank scan
+  int64_t* digit_base = nullptr;             // [65536] scratch of the virtual-rank scan
   int64_t* mybase_v = nullptr;               // [V][65536]
   int64_t* localbase_v = nullptr;            // [V][65536]
   int64_t* bases_v = nullptr;                // [V][2][257]
-  int64_t* seg_start_v = nullptr;            // [V][2] = {0, m_q}
-  uint32_t* seg_tiles_v = nullptr;           // [V][2] = {0, tiles of part q}
   int dense_ready_digit = -1;                // digit whose dense counts already sit in c_all
   cudaStream_t xstream = nullptr;            // exchange stream (highest priority)
-  cudaEvent_t ev_sorted[8] = {}, ev_xs[8] = {}, ev_x[8] = {};
-  double exchange_ms_acc = 0;
-  uint32_t* seg_tile_start = nullptr;        // [257]
-  int64_t* one_seg_start = nullptr;          // {0, here}
-  uint32_t* one_seg_tiles = nullptr;         // {0, ceil(here/TILE)}
+  cudaEvent_t ev_sorted[LSB_MAX_PARTS] = {}, ev_x[LSB_MAX_PARTS] = {};
+  std::vector<cudaEvent_t> xev;              // exchange kernel start/stop pairs (LSB_FLAG_PHASE_EVENTS)
   unsigned long long* small = nullptr;       // [64] scratch: sent[8], verify[5], barrier word, gather
   unsigned long long* small_all = nullptr;   // [G][16]
   unsigned long long* host_small = nullptr;  // pinned [8*16 + 64]
@@ -102,15 +131,16 @@ struct lsb_ctx {
   bool comm_ready = false;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   std::vector<cudaEvent_t> phase_ev;
-  std::vector<int> phase_kind;  // 0 hist, 1 scan/collective, 2 partition
+  std::vector<int> phase_kind;  // 0 count, 1 scan/collective, 2 scatter (one-pass / partition), 3 exchange
   int64_t launches = 0;
   int64_t part_elems = 0;
   int skipped = 0;
-  unsigned long long* host_hist = nullptr;  // pinned [HIST_MAX_SUB][256]
   std::string err;
 };
 
 namespace {
+
+constexpr int TILE_COUNTERS = 1024;
 
 thread_local std::string g_create_err;
 
@@ -173,7 +203,9 @@ PassPlan plan_pass(const lsb_ctx* c, int digit) {
   PassPlan p;
   p.shift = c->cfg.radix_bits * digit;
   p.bits = std::min<int>(c->cfg.radix_bits, 64 - p.shift);
-  p.lo_bits = p.bits > 8 ? p.bits / 2 : 0;  // balanced split: fewer bins per step = longer runs per bin
+  // one-pass kernel: low BYTE, then the rest; two-step shape: balanced split (longer runs per bin)
+  if (p.bits <= 8) p.lo_bits = 0;
+  else p.lo_bits = (c->cfg.flags & LSB_FLAG_TWO_STEP) ? p.bits / 2 : 8;
   p.hi_bits = p.bits - p.lo_bits;
   return p;
 }
@@ -190,22 +222,28 @@ int phase_mark(lsb_ctx* c, int kind) {
 
 int begin_call(lsb_ctx* c) {
   for (auto ev : c->phase_ev) cudaEventDestroy(ev);
+  for (auto ev : c->xev) cudaEventDestroy(ev);
   c->phase_ev.clear();
   c->phase_kind.clear();
+  c->xev.clear();
   c->launches = 0;
   c->part_elems = 0;
   c->skipped = 0;
   c->next_counter = 0;
-  CU(c, cudaMemsetAsync(c->tile_counters, 0, 256 * sizeof(uint32_t), c->stream));
-  c->exchange_ms_acc = 0;
+  CU(c, cudaMemsetAsync(c->tile_counters, 0, TILE_COUNTERS * sizeof(uint32_t), c->stream));
+  CU(c, cudaMemsetAsync(c->op_err, 0, sizeof(unsigned), c->stream));
   CU(c, cudaEventRecord(c->ev_start, c->stream));
   return phase_mark(c, -1);
 }
 
 int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
   CU(c, cudaEventRecord(c->ev_stop, c->stream));
+  CU(c, cudaMemcpyAsync(c->host_small + 8, c->op_err, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  if (c->G > 1) CU(c, cudaMemcpyAsync(c->host_small, c->small, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaGetLastError());
+  if (*reinterpret_cast<unsigned*>(c->host_small + 8))
+    return fail(c, LSB_ERR_STATE, "one-pass kernel: a wait on another tile timed out (watchdog); the result is void");
   if (!st) return LSB_OK;
   memset(st, 0, sizeof(*st));
   float ms = 0;
@@ -223,19 +261,22 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
     switch (c->phase_kind[i]) {
       case 0: st->hist_ms += d; break;
       case 1: st->scan_ms += d; break;
-      case 3: st->exchange_ms += d; break;
       case 2:
         st->partition_ms += d;
         if (sp < LSB_MAX_SUBPASSES) st->subpass_ms[sp] = d;
         sp++;
         break;
+      default: break;  // 3: the tail of a pipelined pass waiting for its last exchange
     }
+  }
+  for (size_t i = 0; i + 1 < c->xev.size(); i += 2) {
+    float d = 0;
+    CU(c, cudaEventElapsedTime(&d, c->xev[i], c->xev[i + 1]));
+    st->exchange_ms += d;
   }
   st->partition_launches = subpasses;
   st->partition_elements = c->part_elems;
-  if (c->exchange_ms_acc > 0) st->exchange_ms = c->exchange_ms_acc;
   if (c->G > 1) {
-    CU(c, cudaMemcpy(c->host_small, c->small, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     for (int g = 0; g < c->G; g++) st->sent[g] = (int64_t)c->host_small[g];
   } else {
     st->sent[0] = c->here;
@@ -245,118 +286,158 @@ int end_call(lsb_ctx* c, lsb_stats* st, int passes, int subpasses) {
 
 // ---- kernel launch helpers -----------------------------------------------------------
 
-int launch_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
-  // hist[] holds nsub 256-bin histograms; more than HIST_MAX_SUB sub-digits => several reads
-  CU(c, cudaMemsetAsync(c->hist, 0, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, c->stream));
-  if (c->here > 0) {
-    HistArgs a;
+// counts of `ndig` digits over src[0, m) in ONE read (localShuffle's count loop, :226-229):
+// digit i of width bits[i] at shift[i] is accumulated into out[out_off[i] ...] (u64 or u32
+// bins, the caller zeroes them).  Digits are packed into at most 4 roles of <= 65 536 bins.
+int launch_digit_hist(lsb_ctx* c, const Elt* src, int64_t m, const int* shift, const int* bits, const int* out_off, int ndig,
+                      void* out, bool out_u32) {
+  for (int first = 0; first < ndig;) {
+    DigitHistArgs a;
     memset(&a, 0, sizeof(a));
     a.src = src;
-    a.m = c->here;
-    a.nsub = nsub;
-    for (int s = 0; s < nsub; s++) {
-      a.shift[s] = subs[s].shift;
-      a.mask[s] = (1u << subs[s].bits) - 1;
+    a.m = m;
+    a.out = out;
+    a.out_u32 = out_u32 ? 1 : 0;
+    int nd = 0, role = 0, role_bins = 0;
+    a.role_first[0] = 0;
+    while (first + nd < ndig && nd < DH_MAX_DIGITS) {
+      const int nb = 1 << bits[first + nd];
+      if (role_bins + nb > 65536) {
+        if (role == 3) break;
+        a.role_first[++role] = nd;
+        role_bins = 0;
+      }
+      a.shift[nd] = shift[first + nd];
+      a.mask[nd] = (uint32_t)(nb - 1);
+      a.smem_off[nd] = role_bins;
+      a.out_off[nd] = out_off[first + nd];
+      role_bins += nb;
+      nd++;
     }
-    a.out = c->hist;
-    int grid = (int)std::min<int64_t>(148 * 4, div_ceil(c->here, HIST_THREADS));
-    bool bytes = true;  // sub-digits are exactly bytes 0..nsub-1 of the key (radix 8 and 16)
-    for (int s = 0; s < nsub; s++) bytes = bytes && subs[s].shift == 8 * s && subs[s].bits == 8;
-#define LSB_HIST(N, B) hist_kernel<N, B><<<grid, HIST_THREADS, 0, c->stream>>>(a)
-    if (bytes && nsub == 8) LSB_HIST(8, true);
-    else switch (nsub) {
-      case 1: LSB_HIST(1, false); break;
-      case 2: LSB_HIST(2, false); break;
-      case 3: LSB_HIST(3, false); break;
-      case 4: LSB_HIST(4, false); break;
-      case 5: LSB_HIST(5, false); break;
-      case 6: LSB_HIST(6, false); break;
-      case 7: LSB_HIST(7, false); break;
-      case 8: LSB_HIST(8, false); break;
-      case 9: LSB_HIST(9, false); break;
-      case 10: LSB_HIST(10, false); break;
-      case 11: LSB_HIST(11, false); break;
-      case 12: LSB_HIST(12, false); break;
-      case 13: LSB_HIST(13, false); break;
-      case 14: LSB_HIST(14, false); break;
-      case 15: LSB_HIST(15, false); break;
-      default: LSB_HIST(16, false); break;
+    a.nroles = role + 1;
+    for (int r = a.nroles; r < 5; r++) a.role_first[r] = nd;
+    if (m > 0) {
+      const int64_t chunks = div_ceil(m, (int64_t)DH_THREADS * 8);
+      const int groups = (int)std::max<int64_t>(1, std::min<int64_t>(c->num_sms / a.nroles, chunks));
+      bool one_each = true;
+      for (int r = 0; r < a.nroles; r++) one_each = one_each && (a.role_first[r + 1] - a.role_first[r] == 1);
+      if (one_each) digit_hist_kernel<1><<<groups * a.nroles, DH_THREADS, DH_SMEM, c->stream>>>(a);
+      else digit_hist_kernel<0><<<groups * a.nroles, DH_THREADS, DH_SMEM, c->stream>>>(a);
+      c->launches++;
+      CU(c, cudaGetLastError());
     }
-#undef LSB_HIST
-    c->launches++;
+    first += nd;
   }
-  CU(c, cudaGetLastError());
-  int rc = phase_mark(c, 0);
-  if (rc) return rc;
-  scan256_kernel<<<nsub, 256, 0, c->stream>>>(c->hist, c->scan_out);
-  c->launches++;
-  CU(c, cudaGetLastError());
-  return phase_mark(c, 1);
+  return LSB_OK;
 }
 
-int launch_partition(lsb_ctx* c, const Elt* src, int shift, int bits, int seg_bits, const int64_t* seg_start,
-                     const uint32_t* seg_tile_start, const int64_t* bases, int dst_buf, bool global_dst,
-                     int full_shift = -1, int full_bits = 0, int64_t m_override = -1, Elt* dst_override = nullptr) {
+// exclusive scan of counts[G][nb] in digit-major, rank-minor order -> out[nb] = this rank's column
+int launch_scan(lsb_ctx* c, const unsigned long long* counts, int nb, int G, int my, int64_t* out, unsigned long long* sent) {
+  GlobalScanArgs s;
+  s.counts = counts;
+  s.nb = nb;
+  s.G = G;
+  s.my = my;
+  s.per = sent ? c->per : INT64_MAX / 16;
+  s.mybase = out;
+  s.sent = sent;
+  global_scan_kernel<<<1, 1024, 0, c->stream>>>(s);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return LSB_OK;
+}
+
+// one stable counting-sort step on <= 8 bits over src[0, m): the whole pass for digits of <= 8
+// bits, half a pass in the two-step shape.  bases[bin] = first output index of the bin.
+int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits, const int64_t* bases, Elt* dst) {
   if (c->gen > 126) {  // tags exhausted: wipe the look-back words and start over
     CU(c, cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
     c->gen = 0;
   }
-  if (c->next_counter >= 256) return fail(c, LSB_ERR_STATE, "too many partition launches in one call");
+  if (c->next_counter >= TILE_COUNTERS) {  // stream order: every earlier launch is done with its counter
+    CU(c, cudaMemsetAsync(c->tile_counters, 0, TILE_COUNTERS * sizeof(uint32_t), c->stream));
+    c->next_counter = 0;
+  }
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.src = src;
+  a.m = m;
   a.shift = shift;
   a.mask = (1u << bits) - 1;
-  a.seg_bits = seg_bits;
-  a.seg_start = seg_start;
-  a.seg_tile_start = seg_tile_start;
   a.bases = bases;
   a.lookback = c->lookback;
   a.tile_counter = c->tile_counters + c->next_counter++;
   a.tag_agg = (uint64_t)(2 * c->gen + 1) << 56;
   a.tag_inc = (uint64_t)(2 * c->gen + 2) << 56;
   c->gen++;
-  if (global_dst) {
-    a.per = c->per;
-    a.world = c->G;
-    for (int g = 0; g < c->G; g++) a.dst[g] = c->peer[dst_buf][g];
-  } else {
-    a.per = INT64_MAX / 16;
-    a.world = 1;
-    a.dst[0] = dst_override ? dst_override : c->buf[dst_buf];
-  }
-  const int64_t m_launch = m_override >= 0 ? m_override : c->here;
-  const int64_t max_tiles = div_ceil(m_launch, c->tile) + (seg_bits ? (1 << seg_bits) : 0);
-  c->part_elems += m_launch;
-  if (m_launch > 0) {
-    const bool runs = full_shift >= 0;
-    if (runs) {
-      a.run_counts = c->counts_local;
-      a.full_shift = full_shift;
-      a.full_mask = (1u << full_bits) - 1;
-    }
-    static const int extra_smem = getenv("LSB_PT_EXTRA_SMEM") ? atoi(getenv("LSB_PT_EXTRA_SMEM")) : 0;  // experiment: force 1 CTA/SM
-#define LSB_PART(CFG)                                                                                         \
-    if (runs) partition_kernel<CFG, true><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM + extra_smem, c->stream>>>(a);     \
-    else partition_kernel<CFG, false><<<(unsigned)max_tiles, CFG::THREADS, CFG::SMEM + extra_smem, c->stream>>>(a)
-    if (c->variant == 6) {  // persistent kernel: one CTA per SM, single-segment inputs only
-      if (seg_bits) return fail(c, LSB_ERR_STATE, "persistent partition kernel needs a single segment");
-      const unsigned grid = (unsigned)std::min<int64_t>(c->num_sms, div_ceil(m_launch, c->tile));
-      if (runs) partition_persistent_kernel<PersistCfgA, true><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
-      else partition_persistent_kernel<PersistCfgA, false><<<grid, PersistCfgA::THREADS, PersistCfgA::SMEM, c->stream>>>(a);
-    } else
-    switch (c->variant) {
-      case 0: LSB_PART(PartCfgA); break;
-      case 1: LSB_PART(PartCfgB); break;
-      case 2: LSB_PART(PartCfgC); break;
-      case 3: LSB_PART(PartCfgD); break;
-      case 5: LSB_PART(PartCfgF); break;
-      default: LSB_PART(PartCfgE); break;
-    }
-#undef LSB_PART
+  a.dst = dst;
+  c->part_elems += m;
+  if (m > 0) {
+    partition_kernel<TileCfg><<<(unsigned)div_ceil(m, c->tile), TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
     c->launches++;
   }
   CU(c, cudaGetLastError());
+  return phase_mark(c, 2);
+}
+
+// one stable scatter on a digit of 9..16 bits over src[0, m) -> dst: starts[d] + add is the first
+// output index of digit d (natural digit order); `ctas_per_sm` 0 = as many as stay resident
+int launch_onepass(lsb_ctx* c, const Elt* src, Elt* dst, int64_t m, int shift, int bits, const int64_t* starts, long long add,
+                   int ctas_per_sm) {
+  c->part_elems += m;
+  if (m > 0) {
+    const int T1 = c->tune.op_t1, NX = c->tune.op_nx;
+    const int nsuper = (int)div_ceil(m, c->op_S);
+    // control block layout for this launch (u32 words), then the look-back ring (u64)
+    size_t w = 0;
+    auto take = [&](size_t n) { size_t o = w; w += n; return o; };
+    const size_t o_ticket = take(4), o_done1 = take(nsuper), o_done2 = take(nsuper), o_ready2 = take(nsuper),
+                 o_limit2 = take(nsuper), o_totals = take(256 * (size_t)nsuper), o_segrow = take(256 * (size_t)nsuper),
+                 o_subclaim = take(256 * (size_t)nsuper), o_biglist = take(256 * (size_t)nsuper);
+    w = (w + 3) & ~(size_t)3;
+    const size_t ring_bytes = (size_t)NX * (T1 + 256) * 256 * sizeof(uint64_t);
+    const size_t bytes = w * 4 + ring_bytes;
+    if (bytes > c->op_ctl_bytes) return fail(c, LSB_ERR_STATE, "one-pass control block too small");
+    CU(c, cudaMemsetAsync(c->op_ctl, 0, bytes, c->stream));
+    onepass_prep_kernel<<<256, 256, 0, c->stream>>>(starts, 1 << bits, add, c->op_F);
+    OnePassArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src;
+    a.dst = dst;
+    a.m = m;
+    a.shift = shift;
+    a.hi_bits = bits - 8;
+    a.T1 = T1;
+    a.NX = NX;
+    a.nsuper = nsuper;
+    a.lead = c->tune.op_lead;
+    a.hints = c->tune.op_hints;
+    a.X = c->op_X;
+    a.oc = c->op_oc;
+    unsigned* ctl = reinterpret_cast<unsigned*>(c->op_ctl);
+    a.lookback = reinterpret_cast<uint64_t*>(c->op_ctl + w * 4);
+    a.F = c->op_F;
+    a.err = c->op_err;
+    a.ticket = ctl + o_ticket;
+    a.done1 = ctl + o_done1;
+    a.done2 = ctl + o_done2;
+    a.ready2 = ctl + o_ready2;
+    a.limit2 = ctl + o_limit2;
+    a.totals = ctl + o_totals;
+    a.segrow = ctl + o_segrow;
+    a.subclaim = ctl + o_subclaim;
+    a.biglist = ctl + o_biglist;
+    a.timeout_ns = (unsigned long long)c->tune.timeout_ms * 1000000ULL;
+    a.prof = c->op_prof;
+    const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, c->op_resident) : c->op_resident;
+    // every claimed item must belong to a resident CTA: never launch more CTAs than fit
+    const int64_t useful = div_ceil(m, c->op_tile) + 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->num_sms * per_sm, useful));
+    if (c->tune.op_cfg == 1) onepass_kernel<TileCfgS><<<grid, TileCfgS::THREADS, TileCfgS::SMEM, c->stream>>>(a);
+    else onepass_kernel<TileCfg><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+    c->launches += 2;
+    CU(c, cudaGetLastError());
+  }
   return phase_mark(c, 2);
 }
 
@@ -367,262 +448,84 @@ int stream_barrier(lsb_ctx* c) {
   return LSB_OK;
 }
 
-// counts of a full digit of this shard -> all-gather -> digit-major/rank-minor scan -> mybase[]
-int global_offsets(lsb_ctx* c, int nb) {
-  const unsigned long long* all = c->counts_local;
-  if (c->G > 1) {
-    NC(c, g_nccl.AllGather(c->counts_local, c->counts_all, (size_t)nb, ncclUint64, c->comm, c->stream));
-    all = c->counts_all;
+int64_t part_len(const lsb_ctx* c, int q) {
+  return std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart));
+}
+
+// virtual-rank counts of digit `digit` for every part of every GPU -> c_all[G*V][nb]
+// (localShuffle's counts, :226-229, per part; then the count exchange of :327-383)
+int count_parts(lsb_ctx* c, int digit) {
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits, V = c->V;
+  CU(c, cudaMemsetAsync(c->dense_local, 0, sizeof(unsigned) * (size_t)V * nb, c->stream));
+  for (int q = 0; q < V; q++) {
+    const int64_t m = part_len(c, q);
+    if (m <= 0) continue;
+    const int off = q * nb;
+    int rc = launch_digit_hist(c, c->buf[c->cur] + (int64_t)q * c->vpart, m, &p.shift, &p.bits, &off, 1, c->dense_local, true);
+    if (rc) return rc;
   }
+  if (c->G > 1) {
+    NC(c, g_nccl.AllGather(c->dense_local, c->c_all, (size_t)V * nb, ncclUint32, c->comm, c->stream));
+  } else {
+    CU(c, cudaMemcpyAsync(c->c_all, c->dense_local, sizeof(unsigned) * (size_t)V * nb, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return LSB_OK;
+}
+
+// c_all -> mybase_v[q][d] (global output index of part q's first element of digit d: the
+// reference's exclusive scan in digit-major / rank-minor order, :327-479, over virtual ranks),
+// sent[] (:553-554), localbase_v and the bases of the local step(s) of every part
+int part_offsets(lsb_ctx* c, int digit) {
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits, V = c->V;
   CU(c, cudaMemsetAsync(c->small, 0, 8 * sizeof(unsigned long long), c->stream));
-  GlobalScanArgs s;
-  s.counts = all;
-  s.nb = nb;
-  s.G = c->G;
-  s.my = c->my;
-  s.per = c->per;
-  s.mybase = c->mybase;
-  s.sent = c->small;
-  global_scan_kernel<<<1, 1024, 0, c->stream>>>(s);
+  VrScanArgs v;
+  v.counts = c->c_all;
+  v.nb = nb;
+  v.GV = c->G * V;
+  v.first_vr = c->my * V;
+  v.V = V;
+  v.G = c->G;
+  v.per = c->per;
+  v.totals = c->totals;
+  v.digit_base = c->digit_base;
+  v.mybase = c->mybase_v;
+  v.sent = c->small;
+  vr_totals_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
   c->launches++;
+  int rc = launch_scan(c, c->totals, nb, 1, 0, c->digit_base, nullptr);
+  if (rc) return rc;
+  vr_place_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
+  PartPrepArgs pp;
+  pp.counts = c->c_all + (size_t)c->my * V * nb;
+  pp.nb = nb;
+  pp.lo_bits = p.lo_bits;
+  pp.hi_bits = p.hi_bits;
+  pp.localbase = c->localbase_v;
+  pp.bases = c->bases_v;
+  part_prep_kernel<<<V, 1024, 0, c->stream>>>(pp);
+  c->launches += 2;
   CU(c, cudaGetLastError());
   return LSB_OK;
 }
 
-// one reference pass, multi-GPU shape (also correct for G == 1), exchange by direct scatter:
-// the high sub-digit step stores its runs straight into the peers (LSB_FLAG_DIRECT_SCATTER)
-int pass_global_direct(lsb_ctx* c, int digit, int* subpasses) {
-  const PassPlan p = plan_pass(c, digit);
-  const int other = c->cur ^ 1;
-  const Elt* src2 = c->buf[c->cur];
-  int dst_buf = other;
-  const int64_t* seg_start = c->one_seg_start;
-  const uint32_t* seg_tiles = c->one_seg_tiles;
-  int rc;
-  if (p.lo_bits > 0) {
-    SubPass lo{p.shift, p.lo_bits};
-    if ((rc = launch_hist(c, c->buf[c->cur], &lo, 1))) return rc;
-    // scan_out[0..256] = segment starts of the shard once grouped by the low bits
-    if ((rc = launch_partition(c, c->buf[c->cur], p.shift, p.lo_bits, 0, c->one_seg_start, c->one_seg_tiles,
-                               c->scan_out, other, false)))
-      return rc;
-    (*subpasses)++;
-    seg_tiles_kernel<<<1, 256, 0, c->stream>>>(c->scan_out, 1 << p.lo_bits, c->tile, c->seg_tile_start);
-    c->launches++;
-    CU(c, cudaGetLastError());
-    src2 = c->buf[other];
-    dst_buf = c->cur;
-    seg_start = c->scan_out;
-    seg_tiles = c->seg_tile_start;
-  }
-  const int nb = 1 << p.bits;
-  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
-  if (c->here > 0) {
-    SegCountArgs sc;
-    sc.src = src2;
-    sc.m = c->here;
-    sc.seg_start = seg_start;
-    sc.lo_bits = p.lo_bits;
-    sc.shift_hi = p.shift + p.lo_bits;
-    sc.mask_hi = (1u << p.hi_bits) - 1;
-    sc.out = c->counts_local;
-    int grid = (int)std::min<int64_t>(148 * 4, div_ceil(c->here, HIST_THREADS));
-    seg_count_kernel<<<grid, HIST_THREADS, 0, c->stream>>>(sc);
-    c->launches++;
-    CU(c, cudaGetLastError());
-  }
-  if ((rc = phase_mark(c, 0))) return rc;
-  // the all-gather doubles as the barrier "every GPU is done reading the shard that is
-  // about to be overwritten by its peers"
-  if ((rc = global_offsets(c, nb))) return rc;
-  if ((rc = phase_mark(c, 1))) return rc;
-  if ((rc = launch_partition(c, src2, p.shift + p.lo_bits, p.hi_bits, p.lo_bits, seg_start, seg_tiles, c->mybase,
-                             dst_buf, true)))
-    return rc;
-  (*subpasses)++;
-  // peers' stores into my shard must have landed before anything reads it
-  if ((rc = stream_barrier(c))) return rc;
-  c->cur = dst_buf;
-  return LSB_OK;
-}
-
-// one reference pass, multi-GPU shape (also correct for G == 1):
-//   1. ONE read counts both sub-digits of the shard (256 bins each);
-//   2. local stable step on the low bits, local stable step on the high bits: the shard is sorted
-//      by the full digit (== localShuffle, :213-247); the second step also emits the shard's
-//      counts of the full digit from the runs it writes (== counts, :226-229);
-//   3. count all-gather + digit-major/rank-minor scan (== :327-479);
-//   4. exchange kernel: every run goes to its global position in the owning GPU's shard (== :530-576).
-int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next);
-
-int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
-  if (c->cfg.flags & LSB_FLAG_DIRECT_SCATTER) return pass_global_direct(c, digit, subpasses);
-  if (c->pipelined) return pass_global_pipelined(c, digit, subpasses, fuse_next);
-  const PassPlan p = plan_pass(c, digit);
-  const int nb = 1 << p.bits;
-  int rc;
-  SubPass subs[2];
-  int ns = 0;
-  if (p.lo_bits) subs[ns++] = {p.shift, p.lo_bits};
-  subs[ns++] = {p.shift + p.lo_bits, p.hi_bits};
-  if (c->hist_ready_digit == digit) {  // the previous pass's exchange already counted this pass's sub-digits
-    scan256_kernel<<<ns, 256, 0, c->stream>>>(c->hist, c->scan_out);
-    c->launches++;
-    CU(c, cudaGetLastError());
-  } else if ((rc = launch_hist(c, c->buf[c->cur], subs, ns))) {
-    return rc;
-  }
-  c->hist_ready_digit = -1;
-  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
-  for (int s = 0; s < ns; s++) {
-    const bool last = (s == ns - 1);
-    if ((rc = launch_partition(c, c->buf[c->cur], subs[s].shift, subs[s].bits, 0, c->one_seg_start, c->one_seg_tiles,
-                               c->scan_out + (size_t)s * 257, c->cur ^ 1, false, last ? p.shift : -1, p.bits)))
-      return rc;
-    c->cur ^= 1;
-    (*subpasses)++;
-  }
-  // local offsets of every digit: exclusive scan of this shard's counts in digit order
-  {
-    GlobalScanArgs s;
-    s.counts = c->counts_local;
-    s.nb = nb;
-    s.G = 1;
-    s.my = 0;
-    s.per = INT64_MAX / 16;
-    s.mybase = c->localbase;
-    s.sent = nullptr;
-    global_scan_kernel<<<1, 1024, 0, c->stream>>>(s);
-    c->launches++;
-    CU(c, cudaGetLastError());
-  }
-  // queued after the local sort, the all-gather is also the barrier "every GPU is done reading the
-  // buffer its peers are about to overwrite"
-  if ((rc = global_offsets(c, nb))) return rc;
-  if ((rc = phase_mark(c, 1))) return rc;
-  const int xbuf = c->cur ^ 1;
-  SubPass nsubs[2];
-  int next_ns = 0;
-  if (fuse_next && digit + 1 < c->npasses) {
-    const PassPlan q = plan_pass(c, digit + 1);
-    if (q.lo_bits) nsubs[next_ns++] = {q.shift, q.lo_bits};
-    nsubs[next_ns++] = {q.shift + q.lo_bits, q.hi_bits};
-    CU(c, cudaMemsetAsync(c->next_hist, 0, sizeof(unsigned long long) * 512 * c->G, c->stream));
-  }
-  if (c->here > 0) {
-    ExchArgs x;
-    memset(&x, 0, sizeof(x));
-    x.src = c->buf[c->cur];
-    x.m = c->here;
-    x.shift = p.shift;
-    x.mask = (uint32_t)(nb - 1);
-    x.localbase = c->localbase;
-    x.mybase = c->mybase;
-    x.per = c->per;
-    x.world = c->G;
-    for (int g = 0; g < c->G; g++) x.dst[g] = c->peer[xbuf][g];
-    if (next_ns) {
-      x.next_nsub = next_ns;
-      for (int s = 0; s < next_ns; s++) {
-        x.next_shift[s] = nsubs[s].shift;
-        x.next_mask[s] = (1u << nsubs[s].bits) - 1;
-      }
-      x.next_hist = c->next_hist;
-    }
-    static const int ex_mult = getenv("LSB_EX_GRID") ? atoi(getenv("LSB_EX_GRID")) : 8;  // CTAs per SM worth of grid
-    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * ex_mult, div_ceil(c->here, (int64_t)EX_THREADS * EX_U));
-    exchange_kernel<<<grid, EX_THREADS, 0, c->stream>>>(x);
-    c->launches++;
-    CU(c, cudaGetLastError());
-  }
-  if ((rc = phase_mark(c, 3))) return rc;
-  if (next_ns) {
-    // all-gather of the per-destination counts: also the barrier "all peers' stores into my shard landed"
-    if (c->G > 1) {
-      NC(c, g_nccl.AllGather(c->next_hist, c->next_hist_all, (size_t)512 * c->G, ncclUint64, c->comm, c->stream));
-    } else {
-      CU(c, cudaMemcpyAsync(c->next_hist_all, c->next_hist, sizeof(unsigned long long) * 512, cudaMemcpyDeviceToDevice, c->stream));
-    }
-    next_hist_reduce_kernel<<<1, 512, 0, c->stream>>>(c->next_hist_all, c->G, c->my, c->hist);
-    c->launches++;
-    CU(c, cudaGetLastError());
-    c->hist_ready_digit = digit + 1;
-    if ((rc = phase_mark(c, 1))) return rc;
-  } else if ((rc = stream_barrier(c))) {  // peers' stores into my shard must have landed before anything reads it
-    return rc;
-  }
-  c->cur = xbuf;
-  return LSB_OK;
-}
-
-// one reference pass, multi-GPU, pipelined over V parts of the shard (virtual ranks g*V+q):
+// one reference pass, pipelined over V parts of the shard (virtual ranks g*V+q):
 //   counts of the full digit of every part are known up front (first pass: counted here; later
 //   passes: produced by the previous pass's exchange kernel), so
-//     part q:   local low step, local high step (compute stream)  ->  exchange (exchange stream)
+//     part q:   local stable sort by the digit (compute stream)  ->  exchange (exchange stream)
 //   and the exchange of part q overlaps the local sort of part q+1.
-int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
+int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
   const PassPlan p = plan_pass(c, digit);
   const int nb = 1 << p.bits;
   const int V = c->V;
   int rc;
-  auto part_len = [&](int q) { return std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart)); };
-
   if (c->dense_ready_digit != digit) {  // nobody has counted this digit yet
-    CU(c, cudaMemsetAsync(c->dense_local, 0, sizeof(unsigned) * (size_t)V * nb, c->stream));
-    for (int q = 0; q < V; q++) {
-      const int64_t m = part_len(q);
-      if (m <= 0) continue;
-      dense_count32_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->buf[c->cur] + (int64_t)q * c->vpart, m, p.shift,
-                                                               (uint32_t)(nb - 1), c->dense_local + (size_t)q * nb);
-      c->launches++;
-    }
-    CU(c, cudaGetLastError());
-    if (c->G > 1) {
-      NC(c, g_nccl.AllGather(c->dense_local, c->c_all, (size_t)V * nb, ncclUint32, c->comm, c->stream));
-    } else {
-      CU(c, cudaMemcpyAsync(c->c_all, c->dense_local, sizeof(unsigned) * (size_t)V * nb, cudaMemcpyDeviceToDevice, c->stream));
-    }
+    if ((rc = count_parts(c, digit))) return rc;
     if ((rc = phase_mark(c, 0))) return rc;
   }
   c->dense_ready_digit = -1;
-
-  CU(c, cudaMemsetAsync(c->small, 0, 8 * sizeof(unsigned long long), c->stream));
-  {
-    VrScanArgs v;
-    v.counts = c->c_all;
-    v.nb = nb;
-    v.GV = c->G * V;
-    v.first_vr = c->my * V;
-    v.V = V;
-    v.G = c->G;
-    v.per = c->per;
-    v.totals = c->counts_local;                          // [nb] u64 scratch
-    v.digit_base = c->localbase;                         // [nb] i64 scratch
-    v.mybase = c->mybase_v;
-    v.sent = c->small;
-    vr_totals_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
-    GlobalScanArgs gs;
-    gs.counts = c->counts_local;
-    gs.nb = nb;
-    gs.G = 1;
-    gs.my = 0;
-    gs.per = INT64_MAX / 16;
-    gs.mybase = c->localbase;
-    gs.sent = nullptr;
-    global_scan_kernel<<<1, 1024, 0, c->stream>>>(gs);
-    vr_place_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
-    c->launches += 2;
-    PartPrepArgs pp;
-    pp.counts = c->c_all + (size_t)c->my * V * nb;
-    pp.nb = nb;
-    pp.lo_bits = p.lo_bits;
-    pp.hi_bits = p.hi_bits;
-    pp.localbase = c->localbase_v;
-    pp.bases = c->bases_v;
-    part_prep_kernel<<<V, 1024, 0, c->stream>>>(pp);
-    c->launches += 2;
-    CU(c, cudaGetLastError());
-  }
+  if ((rc = part_offsets(c, digit))) return rc;
   if ((rc = phase_mark(c, 1))) return rc;
 
   int next_nb = 0, next_shift = 0;
@@ -633,35 +536,40 @@ int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next)
     next_shift = q.shift;
     CU(c, cudaMemsetAsync(c->next_dense, 0, sizeof(unsigned) * (size_t)c->G * V * next_nb, c->stream));
   }
-  static const int ex_mult = getenv("LSB_EX_GRID_PIPE") ? atoi(getenv("LSB_EX_GRID_PIPE")) : 1;
+  const bool two_step = p.lo_bits && (c->cfg.flags & LSB_FLAG_TWO_STEP);
+  const bool timed = (c->cfg.flags & LSB_FLAG_PHASE_EVENTS) != 0;
   const int xbuf = c->cur ^ 1;
-  int last_x = -1;
+  int last_x = -1, prev_x = -1;
   for (int q = 0; q < V; q++) {
-    const int64_t m = part_len(q);
+    const int64_t m = part_len(c, q);
     if (m <= 0) continue;
     Elt* part = c->buf[c->cur] + (int64_t)q * c->vpart;
-    const Elt* sorted = part;
-    const int64_t* segs = c->seg_start_v + 2 * q;
-    const uint32_t* tiles = c->seg_tiles_v + 2 * q;
-    if (p.lo_bits) {  // low step into the scratch, high step back in place
-      if ((rc = launch_partition(c, part, p.shift, p.lo_bits, 0, segs, tiles, c->bases_v + ((size_t)q * 2 + 0) * 257, 0, false,
-                                 -1, 0, m, c->scratch[0])))
+    const Elt* sorted;
+    if (two_step) {  // low step into the scratch, high step back in place
+      if ((rc = launch_partition(c, part, m, p.shift, p.lo_bits, c->bases_v + ((size_t)q * 2 + 0) * 257, c->scratch[0])))
         return rc;
-      if ((rc = launch_partition(c, c->scratch[0], p.shift + p.lo_bits, p.hi_bits, 0, segs, tiles,
-                                 c->bases_v + ((size_t)q * 2 + 1) * 257, 0, false, -1, 0, m, part)))
+      if ((rc = launch_partition(c, c->scratch[0], m, p.shift + p.lo_bits, p.hi_bits,
+                                 c->bases_v + ((size_t)q * 2 + 1) * 257, part)))
         return rc;
+      sorted = part;
       (*subpasses) += 2;
-    } else {  // a single step: its output lives in an alternating scratch until it has been exchanged
-      if (q >= 2 && last_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[q - 2], 0));
-      if ((rc = launch_partition(c, part, p.shift, p.hi_bits, 0, segs, tiles, c->bases_v + ((size_t)q * 2 + 1) * 257, 0, false,
-                                 -1, 0, m, c->scratch[q & 1])))
-        return rc;
-      sorted = c->scratch[q & 1];
+    } else {  // one launch; its output lives in an alternating scratch until it has been exchanged
+      Elt* out = c->scratch[q & 1];
+      if (prev_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[prev_x], 0));  // scratch[q & 1] was read by that exchange
+      if (p.lo_bits) rc = launch_onepass(c, part, out, m, p.shift, p.bits, c->localbase_v + (size_t)q * nb, 0, c->tune.op_ctas_mgpu);
+      else rc = launch_partition(c, part, m, p.shift, p.hi_bits, c->bases_v + ((size_t)q * 2 + 1) * 257, out);
+      if (rc) return rc;
+      sorted = out;
       (*subpasses)++;
     }
     CU(c, cudaEventRecord(c->ev_sorted[q], c->stream));
     CU(c, cudaStreamWaitEvent(c->xstream, c->ev_sorted[q], 0));
-    CU(c, cudaEventRecord(c->ev_xs[q], c->xstream));
+    if (timed) {
+      cudaEvent_t e0;
+      CU(c, cudaEventCreate(&e0));
+      CU(c, cudaEventRecord(e0, c->xstream));
+      c->xev.push_back(e0);
+    }
     ExchVrArgs x;
     memset(&x, 0, sizeof(x));
     x.src = sorted;
@@ -680,15 +588,22 @@ int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next)
     x.next_nb = next_nb;
     x.part = c->vpart;
     x.next_dense = c->next_dense;
-    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * ex_mult, div_ceil(m, (int64_t)EX_THREADS * EX_U));
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->tune.ex_ctas, div_ceil(m, (int64_t)EX_THREADS * EX_U));
     exchange_vr_kernel<<<grid, EX_THREADS, 0, c->xstream>>>(x);
     c->launches++;
     CU(c, cudaGetLastError());
+    if (timed) {
+      cudaEvent_t e1;
+      CU(c, cudaEventCreate(&e1));
+      CU(c, cudaEventRecord(e1, c->xstream));
+      c->xev.push_back(e1);
+    }
     CU(c, cudaEventRecord(c->ev_x[q], c->xstream));
+    prev_x = last_x;
     last_x = q;
   }
   if (last_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[last_x], 0));
-  if ((rc = phase_mark(c, 4))) return rc;
+  if ((rc = phase_mark(c, 3))) return rc;
   if (has_next) {
     // sum the G contributions to each of my parts, then share every virtual rank's counts: the two
     // collectives are also the barrier "all peers' stores into my shard have landed"
@@ -707,36 +622,69 @@ int pass_global_pipelined(lsb_ctx* c, int digit, int* subpasses, bool fuse_next)
   return LSB_OK;
 }
 
-// passes [d0, d1) on one GPU: one histogram read for all sub-digits, then the partitions
+// passes [d0, d1) on one GPU: one read counts the digits of every pass, then one launch per pass
+// (two in the LSB_FLAG_TWO_STEP shape) that reads the shard once and writes it once
 int passes_single(lsb_ctx* c, int d0, int d1, int* subpasses) {
-  std::vector<SubPass> subs;
-  for (int d = d0; d < d1; d++) {
-    const PassPlan p = plan_pass(c, d);
-    if (p.lo_bits) subs.push_back({p.shift, p.lo_bits});
-    subs.push_back({p.shift + p.lo_bits, p.hi_bits});
+  const int np = d1 - d0;
+  int shift[64], bits[64], off[64], meta[128];
+  int total = 0;
+  for (int i = 0; i < np; i++) {
+    const PassPlan p = plan_pass(c, d0 + i);
+    shift[i] = p.shift;
+    bits[i] = p.bits;
+    off[i] = total;
+    meta[i] = total;
+    meta[64 + i] = 1 << p.bits;
+    total += 1 << p.bits;
   }
   int rc;
-  for (size_t s0 = 0; s0 < subs.size(); s0 += HIST_MAX_SUB) {
-    const int ns = (int)std::min<size_t>(HIST_MAX_SUB, subs.size() - s0);
-    if ((rc = launch_hist(c, c->buf[c->cur], subs.data() + s0, ns))) return rc;
-    const bool may_skip = !(c->cfg.flags & LSB_FLAG_NO_SKIP) && c->here > 0;
-    if (may_skip) {  // a digit that is constant over the shard makes its stable pass the identity
-      CU(c, cudaMemcpyAsync(c->host_hist, c->hist, sizeof(unsigned long long) * 256 * ns, cudaMemcpyDeviceToHost, c->stream));
-      CU(c, cudaStreamSynchronize(c->stream));
-    }
-    for (int s = 0; s < ns; s++) {
-      const SubPass& sp = subs[s0 + s];
-      if (may_skip) {
-        bool constant = false;
-        for (int b = 0; b < 256; b++) constant = constant || c->host_hist[s * 256 + b] == (unsigned long long)c->here;
-        if (constant) { c->skipped++; continue; }
-      }
-      if ((rc = launch_partition(c, c->buf[c->cur], sp.shift, sp.bits, 0, c->one_seg_start, c->one_seg_tiles,
-                                 c->scan_out + (size_t)s * 257, c->cur ^ 1, false)))
+  CU(c, cudaMemsetAsync(c->hist16, 0, sizeof(unsigned long long) * total, c->stream));
+  if ((rc = launch_digit_hist(c, c->buf[c->cur], c->here, shift, bits, off, np, c->hist16, false))) return rc;
+  if ((rc = phase_mark(c, 0))) return rc;
+  for (int i = 0; i < np; i++)
+    if ((rc = launch_scan(c, c->hist16 + off[i], 1 << bits[i], 1, 0, c->starts16 + off[i], nullptr))) return rc;
+  const bool may_skip = !(c->cfg.flags & LSB_FLAG_NO_SKIP) && c->here > 0;
+  if (may_skip) {  // a digit that is constant over the shard makes its stable pass the identity
+    CU(c, cudaMemcpyAsync(c->dig_meta, meta, sizeof(meta), cudaMemcpyHostToDevice, c->stream));
+    constant_digit_kernel<<<np, 256, 0, c->stream>>>(c->hist16, c->dig_meta, c->dig_meta + 64, (unsigned long long)c->here, c->skip_flags);
+    c->launches++;
+    CU(c, cudaMemcpyAsync(c->host_skip, c->skip_flags, sizeof(int) * np, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // once per sort, before the first pass
+  }
+  if ((rc = phase_mark(c, 1))) return rc;
+  for (int i = 0; i < np; i++) {
+    if (may_skip && c->host_skip[i]) { c->skipped++; continue; }
+    const PassPlan p = plan_pass(c, d0 + i);
+    const int64_t* starts = c->starts16 + off[i];
+    if (p.lo_bits == 0) {
+      rc = launch_partition(c, c->buf[c->cur], c->here, p.shift, p.bits, starts, c->buf[c->cur ^ 1]);
+      (*subpasses)++;
+    } else if (c->cfg.flags & LSB_FLAG_TWO_STEP) {
+      // bases of the two steps folded out of the digit's counts; one "part" = the whole shard
+      PartPrepArgs pp;
+      pp.counts = nullptr;
+      pp.counts64 = c->hist16 + off[i];
+      pp.nb = 1 << p.bits;
+      pp.lo_bits = p.lo_bits;
+      pp.hi_bits = p.hi_bits;
+      pp.localbase = c->localbase_v;
+      pp.bases = c->bases_v;
+      part_prep_kernel<<<1, 1024, 0, c->stream>>>(pp);
+      c->launches++;
+      if ((rc = launch_partition(c, c->buf[c->cur], c->here, p.shift, p.lo_bits, c->bases_v,
+                                 c->buf[c->cur ^ 1])))
         return rc;
-      c->cur ^= 1;
+      rc = launch_partition(c, c->buf[c->cur ^ 1], c->here, p.shift + p.lo_bits, p.hi_bits,
+                            c->bases_v + 257, c->buf[c->cur]);
+      (*subpasses) += 2;
+      if (rc) return rc;
+      continue;  // back in the same buffer
+    } else {
+      rc = launch_onepass(c, c->buf[c->cur], c->buf[c->cur ^ 1], c->here, p.shift, p.bits, starts, 0, 0);
       (*subpasses)++;
     }
+    if (rc) return rc;
+    c->cur ^= 1;
   }
   return LSB_OK;
 }
@@ -771,6 +719,33 @@ const char* lsb_status_string(int s) {
 
 const char* lsb_last_error(const lsb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
+int lsb_tune(const char* key, int value) {
+  if (!key) return LSB_ERR_ARG;
+  const std::string k(key);
+  if (k == "op_t1" && value >= 1 && value <= OP_MAX_T1) g_tune.op_t1 = value;
+  else if (k == "op_cfg" && value >= 0 && value <= 1) g_tune.op_cfg = value;
+  else if (k == "op_persist" && value >= 0) g_tune.op_persist = value;
+  else if (k == "op_nx" && value >= 2 && value <= 8) g_tune.op_nx = value;
+  else if (k == "op_lead" && value >= 1 && value <= 4) g_tune.op_lead = value;
+  else if (k == "op_hints" && value >= 0 && value <= 15) g_tune.op_hints = value;
+  else if (k == "op_ctas_mgpu" && value >= 0 && value <= 4) g_tune.op_ctas_mgpu = value;
+  else if (k == "vparts" && value >= 1 && value <= LSB_MAX_PARTS) g_tune.vparts = value;
+  else if (k == "ex_ctas" && value >= 1 && value <= 8) g_tune.ex_ctas = value;
+  else if (k == "timeout_ms" && value >= 1) g_tune.timeout_ms = value;
+  else return fail(nullptr, LSB_ERR_ARG, "lsb_tune: unknown key or value out of range: " + k);
+  return LSB_OK;
+}
+
+#ifdef LSB_OP_PROF
+// tools/ only: read and clear the one-pass kernel's stage clocks
+int lsb_debug_prof(lsb_ctx* c, unsigned long long* out) {
+  if (!c || !out) return LSB_ERR_ARG;
+  CU(c, cudaMemcpy(out, c->op_prof, sizeof(unsigned long long) * OP_NPROF, cudaMemcpyDeviceToHost));
+  CU(c, cudaMemset(c->op_prof, 0, sizeof(unsigned long long) * OP_NPROF));
+  return LSB_OK;
+}
+#endif
+
 int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   if (!out || !cfg) return fail(nullptr, LSB_ERR_ARG, "null argument");
   *out = nullptr;
@@ -785,6 +760,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
 
   lsb_ctx* c = new lsb_ctx();
   c->cfg = *cfg;
+  c->tune = g_tune;
+  if (c->tune.op_nx <= c->tune.op_lead) c->tune.op_nx = c->tune.op_lead + 1;
   if (c->cfg.ranks == 0) c->cfg.ranks = cfg->world_size;
   if (c->cfg.and_draws < 1) c->cfg.and_draws = 1;
   c->G = cfg->world_size;
@@ -811,6 +788,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   } while (0)
 
   CUC(cudaSetDevice(cfg->device));
+  CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUC(cudaEventCreate(&c->ev_start));
   CUC(cudaEventCreate(&c->ev_stop));
@@ -819,39 +797,66 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->buf[1], shard_bytes));
   c->peer[0][c->my] = c->buf[0];
   c->peer[1][c->my] = c->buf[1];
-  {
-    const char* v = getenv("LSB_PT_VARIANT");
-    c->variant = v ? atoi(v) : 4;  // PartCfgE measured fastest on B200 (profiles/)
-    if (c->variant < 0 || c->variant > 6) c->variant = 4;
-    if (c->variant == 6 && (cfg->flags & LSB_FLAG_DIRECT_SCATTER)) c->variant = 4;  // segmented input
-    const int tiles[7] = {PartCfgA::TILE, PartCfgB::TILE, PartCfgC::TILE, PartCfgD::TILE, PartCfgE::TILE, PartCfgF::TILE,
-                          PersistCfgA::TILE};
-    c->tile = tiles[c->variant];
-  }
-  c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
+  c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 2;
   CUC(cudaMalloc(&c->lookback, c->lookback_tiles * 256 * sizeof(uint64_t)));
   CUC(cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
-  CUC(cudaMalloc(&c->tile_counters, 256 * sizeof(uint32_t)));
-  CUC(cudaMalloc(&c->hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB));
-  CUC(cudaMalloc(&c->scan_out, sizeof(int64_t) * 257 * HIST_MAX_SUB));
-  CUC(cudaMalloc(&c->counts_local, sizeof(unsigned long long) * 65536));
+  CUC(cudaMalloc(&c->tile_counters, TILE_COUNTERS * sizeof(uint32_t)));
+  CUC(cudaMalloc(&c->hist16, sizeof(unsigned long long) * 65536 * 4));
+  CUC(cudaMalloc(&c->starts16, sizeof(int64_t) * 65536 * 4));
+  CUC(cudaMalloc(&c->dig_meta, sizeof(int) * 128));
+  CUC(cudaMalloc(&c->skip_flags, sizeof(int) * 64));
+  CUC(cudaHostAlloc(&c->host_skip, sizeof(int) * 64, cudaHostAllocDefault));
   CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
   CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
-  CUC(cudaMalloc(&c->localbase, sizeof(int64_t) * 65536));
-  CUC(cudaMalloc(&c->next_hist, sizeof(unsigned long long) * 512 * LSB_MAX_GPUS));
-  CUC(cudaMalloc(&c->next_hist_all, sizeof(unsigned long long) * 512 * LSB_MAX_GPUS * LSB_MAX_GPUS));
-  CUC(cudaMalloc(&c->seg_tile_start, sizeof(uint32_t) * 257));
-  CUC(cudaMalloc(&c->one_seg_start, sizeof(int64_t) * 2));
-  CUC(cudaMalloc(&c->one_seg_tiles, sizeof(uint32_t) * 2));
-  {
-    const bool multi = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
-    c->pipelined = multi && !(cfg->flags & (LSB_FLAG_NO_PIPELINE | LSB_FLAG_DIRECT_SCATTER));
-    const char* v = getenv("LSB_VPARTS");
-    c->V = v ? atoi(v) : 8;
-    if (c->V < 1 || c->V > 8) c->V = 8;
-    c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
+  // one-pass kernel: supertile scratch, piece table, control block, frontier table
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
+  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUC(cudaFuncSetAttribute(digit_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DH_SMEM));
+  CUC(cudaFuncSetAttribute(digit_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DH_SMEM));
+  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfgS::SMEM));
+  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfgS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if (c->tune.op_cfg == 1) {
+    c->op_tile = TileCfgS::TILE;
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfgS>, TileCfgS::THREADS, TileCfgS::SMEM));
+  } else {
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfg>, TileCfg::THREADS, TileCfg::SMEM));
   }
-  if (c->pipelined) {
+  if (c->tune.op_persist > 0) {
+    int max_persist = 0;
+    CUC(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, cfg->device));
+    CUC(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)c->tune.op_persist << 20, (size_t)max_persist)));
+  }
+  if (c->op_resident < 1) {
+    fail(nullptr, LSB_ERR_CUDA, "one-pass kernel does not fit an SM");
+    lsb_destroy(c);
+    return LSB_ERR_CUDA;
+  }
+  {
+    const int64_t tiles = div_ceil(c->per, c->op_tile);
+    if (c->tune.op_t1 > tiles) c->tune.op_t1 = (int)std::max<int64_t>(1, tiles);
+    c->op_S = (int64_t)c->tune.op_t1 * c->op_tile;
+    const int64_t nsuper = div_ceil(c->per, c->op_S);
+    const size_t words = 8 + (size_t)nsuper * (4 + 4 * 256);
+    c->op_ctl_bytes = words * 4 + (size_t)c->tune.op_nx * (c->tune.op_t1 + 256) * 256 * sizeof(uint64_t);
+    CUC(cudaMalloc(&c->op_ctl, c->op_ctl_bytes));
+    CUC(cudaMalloc(&c->op_X, (size_t)c->tune.op_nx * c->op_S * sizeof(Elt)));
+    CUC(cudaMalloc(&c->op_oc, (size_t)c->tune.op_nx * 256 * c->tune.op_t1 * sizeof(unsigned)));
+    CUC(cudaMalloc(&c->op_F, sizeof(uint64_t) * 65536));
+    CUC(cudaMalloc(&c->op_err, sizeof(unsigned)));
+    CUC(cudaMalloc(&c->op_prof, sizeof(unsigned long long) * OP_NPROF));
+    CUC(cudaMemsetAsync(c->op_prof, 0, sizeof(unsigned long long) * OP_NPROF, c->stream));
+  }
+  c->two_level = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
+  c->V = c->two_level ? c->tune.vparts : 1;
+  c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
+  {  // tables of the two-step shape (G == 1: one part = the shard) and of the virtual ranks
+    const int V = c->V;
+    CUC(cudaMalloc(&c->localbase_v, sizeof(int64_t) * 65536 * V));
+    CUC(cudaMalloc(&c->bases_v, sizeof(int64_t) * 257 * 2 * V));
+  }
+  if (c->two_level) {
     const int V = c->V;
     CUC(cudaMalloc(&c->scratch[0], (size_t)(c->vpart + 64) * sizeof(Elt)));
     CUC(cudaMalloc(&c->scratch[1], (size_t)(c->vpart + 64) * sizeof(Elt)));
@@ -859,56 +864,21 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
     CUC(cudaMalloc(&c->dense_mine, sizeof(unsigned) * 65536 * V));
     CUC(cudaMalloc(&c->next_dense, sizeof(unsigned) * 65536 * V * c->G));
     CUC(cudaMalloc(&c->c_all, sizeof(unsigned) * 65536 * V * c->G));
+    CUC(cudaMalloc(&c->totals, sizeof(unsigned long long) * 65536));
+    CUC(cudaMalloc(&c->digit_base, sizeof(int64_t) * 65536));
     CUC(cudaMalloc(&c->mybase_v, sizeof(int64_t) * 65536 * V));
-    CUC(cudaMalloc(&c->localbase_v, sizeof(int64_t) * 65536 * V));
-    CUC(cudaMalloc(&c->bases_v, sizeof(int64_t) * 257 * 2 * V));
-    CUC(cudaMalloc(&c->seg_start_v, sizeof(int64_t) * 2 * V));
-    CUC(cudaMalloc(&c->seg_tiles_v, sizeof(uint32_t) * 2 * V));
-    int64_t segs[16];
-    uint32_t tls[16];
-    for (int q = 0; q < V; q++) {
-      const int64_t m = std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart));
-      segs[2 * q] = 0;
-      segs[2 * q + 1] = m;
-      tls[2 * q] = 0;
-      tls[2 * q + 1] = (uint32_t)div_ceil(m, c->tile);
-    }
-    CUC(cudaMemcpyAsync(c->seg_start_v, segs, sizeof(int64_t) * 2 * V, cudaMemcpyHostToDevice, c->stream));
-    CUC(cudaMemcpyAsync(c->seg_tiles_v, tls, sizeof(uint32_t) * 2 * V, cudaMemcpyHostToDevice, c->stream));
-    CUC(cudaStreamSynchronize(c->stream));
     int lo_prio = 0, hi_prio = 0;
     CUC(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
     CUC(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi_prio));
-    for (int q = 0; q < 8; q++) {
+    for (int q = 0; q < V; q++) {
       CUC(cudaEventCreateWithFlags(&c->ev_sorted[q], cudaEventDisableTiming));
-      CUC(cudaEventCreateWithFlags(&c->ev_xs[q], cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->ev_x[q], cudaEventDisableTiming));
     }
   }
   CUC(cudaMalloc(&c->small, sizeof(unsigned long long) * 64));
   CUC(cudaMalloc(&c->small_all, sizeof(unsigned long long) * 16 * LSB_MAX_GPUS));
   CUC(cudaMemsetAsync(c->small, 0, sizeof(unsigned long long) * 64, c->stream));
-  CUC(cudaHostAlloc(&c->host_hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, cudaHostAllocDefault));
   CUC(cudaHostAlloc(&c->host_small, sizeof(unsigned long long) * (16 * LSB_MAX_GPUS + 64), cudaHostAllocDefault));
-  const int64_t seg[2] = {0, c->here};
-  const uint32_t tl[2] = {0, (uint32_t)div_ceil(c->here, c->tile)};
-  CUC(cudaMemcpyAsync(c->one_seg_start, seg, sizeof(seg), cudaMemcpyHostToDevice, c->stream));
-  CUC(cudaMemcpyAsync(c->one_seg_tiles, tl, sizeof(tl), cudaMemcpyHostToDevice, c->stream));
-#define LSB_SET_ATTR(CFG)                                                                                   \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM + 8192)); \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));    \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));  \
-  CUC(cudaFuncSetAttribute(partition_kernel<CFG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  LSB_SET_ATTR(PartCfgA)
-  LSB_SET_ATTR(PartCfgB)
-  LSB_SET_ATTR(PartCfgC)
-  LSB_SET_ATTR(PartCfgD)
-  LSB_SET_ATTR(PartCfgE)
-  LSB_SET_ATTR(PartCfgF)
-  CUC(cudaFuncSetAttribute(partition_persistent_kernel<PersistCfgA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfgA::SMEM));
-  CUC(cudaFuncSetAttribute(partition_persistent_kernel<PersistCfgA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PersistCfgA::SMEM));
-  CUC(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-#undef LSB_SET_ATTR
   CUC(cudaStreamSynchronize(c->stream));
 #undef CUC
   *out = c;
@@ -919,47 +889,25 @@ void lsb_destroy(lsb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->xstream) cudaStreamSynchronize(c->xstream);
   for (int b = 0; b < 2; b++)
     for (int g = 0; g < LSB_MAX_GPUS; g++)
       if (c->peer_open[b][g]) cudaIpcCloseMemHandle(c->peer[b][g]);
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto ev : c->phase_ev) cudaEventDestroy(ev);
-  cudaFree(c->buf[0]);
-  cudaFree(c->buf[1]);
-  cudaFree(c->lookback);
-  cudaFree(c->tile_counters);
-  cudaFree(c->hist);
-  cudaFree(c->scan_out);
-  cudaFree(c->counts_local);
-  cudaFree(c->counts_all);
-  cudaFree(c->mybase);
-  cudaFree(c->localbase);
-  cudaFree(c->next_hist);
-  cudaFree(c->next_hist_all);
-  cudaFree(c->scratch[0]);
-  cudaFree(c->scratch[1]);
-  cudaFree(c->dense_local);
-  cudaFree(c->dense_mine);
-  cudaFree(c->next_dense);
-  cudaFree(c->c_all);
-  cudaFree(c->mybase_v);
-  cudaFree(c->localbase_v);
-  cudaFree(c->bases_v);
-  cudaFree(c->seg_start_v);
-  cudaFree(c->seg_tiles_v);
-  for (int q = 0; q < 8; q++) {
+  for (auto ev : c->xev) cudaEventDestroy(ev);
+  void* dev[] = {c->buf[0], c->buf[1], c->lookback, c->tile_counters, c->hist16, c->starts16, c->dig_meta, c->skip_flags,
+                 c->counts_all, c->mybase, c->op_ctl, c->op_X, c->op_oc, c->op_F, c->op_err, c->op_prof,
+                 c->scratch[0], c->scratch[1], c->dense_local, c->dense_mine, c->next_dense, c->c_all, c->totals, c->digit_base,
+                 c->mybase_v, c->localbase_v, c->bases_v, c->small, c->small_all};
+  for (void* p : dev) cudaFree(p);
+  for (int q = 0; q < LSB_MAX_PARTS; q++) {
     if (c->ev_sorted[q]) cudaEventDestroy(c->ev_sorted[q]);
-    if (c->ev_xs[q]) cudaEventDestroy(c->ev_xs[q]);
     if (c->ev_x[q]) cudaEventDestroy(c->ev_x[q]);
   }
   if (c->xstream) cudaStreamDestroy(c->xstream);
-  cudaFree(c->seg_tile_start);
-  cudaFree(c->one_seg_start);
-  cudaFree(c->one_seg_tiles);
-  cudaFree(c->small);
-  cudaFree(c->small_all);
   if (c->host_small) cudaFreeHost(c->host_small);
-  if (c->host_hist) cudaFreeHost(c->host_hist);
+  if (c->host_skip) cudaFreeHost(c->host_skip);
   if (c->ev_start) cudaEventDestroy(c->ev_start);
   if (c->ev_stop) cudaEventDestroy(c->ev_stop);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -1039,7 +987,6 @@ int lsb_digit_bits(const lsb_ctx* c, int digit) {
 
 int lsb_generate(lsb_ctx* c) {
   if (!c) return LSB_ERR_ARG;
-  c->hist_ready_digit = -1;
   CU(c, cudaSetDevice(c->cfg.device));
   c->cur = 0;
   if (c->here > 0) {
@@ -1067,7 +1014,6 @@ int lsb_generate(lsb_ctx* c) {
 }
 
 int lsb_upload(lsb_ctx* c, const lsb_elt* host, int64_t off, int64_t count) {
-  if (c) c->hist_ready_digit = -1;
   if (!c || (!host && count) || off < 0 || count < 0 || off + count > c->per) return fail(c, LSB_ERR_ARG, "lsb_upload: range");
   CU(c, cudaSetDevice(c->cfg.device));
   if (count) CU(c, cudaMemcpyAsync(c->buf[c->cur] + off, host, (size_t)count * sizeof(Elt), cudaMemcpyHostToDevice, c->stream));
@@ -1106,10 +1052,9 @@ int lsb_sort(lsb_ctx* c, lsb_stats* st) {
   if (rc) return rc;
   CU(c, cudaSetDevice(c->cfg.device));
   if ((rc = begin_call(c))) return rc;
-  c->hist_ready_digit = -1;
   c->dense_ready_digit = -1;
   int subpasses = 0;
-  if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) {
+  if (!c->two_level) {
     if ((rc = passes_single(c, 0, c->npasses, &subpasses))) return rc;
   } else {
     for (int d = 0; d < c->npasses; d++)
@@ -1124,10 +1069,9 @@ int lsb_pass(lsb_ctx* c, int digit, lsb_stats* st) {
   if (digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_pass: digit out of range");
   CU(c, cudaSetDevice(c->cfg.device));
   if ((rc = begin_call(c))) return rc;
-  c->hist_ready_digit = -1;
   c->dense_ready_digit = -1;
   int subpasses = 0;
-  if (c->G == 1 && !(c->cfg.flags & LSB_FLAG_TWO_LEVEL)) rc = passes_single(c, digit, digit + 1, &subpasses);
+  if (!c->two_level) rc = passes_single(c, digit, digit + 1, &subpasses);
   else rc = pass_global(c, digit, &subpasses, false);
   if (rc) return rc;
   return end_call(c, st, 1, subpasses);
@@ -1146,24 +1090,16 @@ int lsb_sort_host(lsb_ctx* c, const lsb_elt* host_in, lsb_elt* host_out, int64_t
   return LSB_OK;
 }
 
-static int dense_counts(lsb_ctx* c, int digit, int* nb_out) {
-  const PassPlan p = plan_pass(c, digit);
-  const int nb = 1 << p.bits;
-  CU(c, cudaMemsetAsync(c->counts_local, 0, sizeof(unsigned long long) * nb, c->stream));
-  if (c->here > 0) {
-    dense_count_kernel<<<148 * 8, 256, 0, c->stream>>>(c->buf[c->cur], c->here, p.shift, (uint32_t)(nb - 1), c->counts_local);
-    CU(c, cudaGetLastError());
-  }
-  *nb_out = nb;
-  return LSB_OK;
-}
-
+// The two test hooks run the PRODUCTION count and scan kernels of the pass shape in use.
 int lsb_histogram(lsb_ctx* c, int digit, int64_t* host_counts) {
   if (!c || !host_counts || digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_histogram: argument");
   CU(c, cudaSetDevice(c->cfg.device));
-  int nb = 0, rc = dense_counts(c, digit, &nb);
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits, zero = 0;
+  CU(c, cudaMemsetAsync(c->hist16, 0, sizeof(unsigned long long) * nb, c->stream));
+  int rc = launch_digit_hist(c, c->buf[c->cur], c->here, &p.shift, &p.bits, &zero, 1, c->hist16, false);
   if (rc) return rc;
-  CU(c, cudaMemcpyAsync(host_counts, c->counts_local, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(host_counts, c->hist16, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return LSB_OK;
 }
@@ -1173,10 +1109,21 @@ int lsb_starts(lsb_ctx* c, int digit, int64_t* host_starts) {
   if (rc) return rc;
   if (!host_starts || digit < 0 || digit >= c->npasses) return fail(c, LSB_ERR_ARG, "lsb_starts: argument");
   CU(c, cudaSetDevice(c->cfg.device));
-  int nb = 0;
-  if ((rc = dense_counts(c, digit, &nb))) return rc;
-  if ((rc = global_offsets(c, nb))) return rc;
-  CU(c, cudaMemcpyAsync(host_starts, c->mybase, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits, zero = 0;
+  const int64_t* src;
+  if (c->two_level) {
+    // a shard's first element of digit d is its first part's first element of digit d
+    if ((rc = count_parts(c, digit))) return rc;
+    if ((rc = part_offsets(c, digit))) return rc;
+    src = c->mybase_v;
+  } else {
+    CU(c, cudaMemsetAsync(c->hist16, 0, sizeof(unsigned long long) * nb, c->stream));
+    if ((rc = launch_digit_hist(c, c->buf[c->cur], c->here, &p.shift, &p.bits, &zero, 1, c->hist16, false))) return rc;
+    if ((rc = launch_scan(c, c->hist16, nb, 1, 0, c->mybase, nullptr))) return rc;
+    src = c->mybase;
+  }
+  CU(c, cudaMemcpyAsync(host_starts, src, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   return LSB_OK;
 }
@@ -1185,7 +1132,7 @@ static int local_verify(lsb_ctx* c) {
   // small[40..44] = checksum[4], violations
   CU(c, cudaMemsetAsync(c->small + 40, 0, 8 * sizeof(unsigned long long), c->stream));
   if (c->here > 0) {
-    int grid = (int)std::min<int64_t>(148 * 8, div_ceil(c->here, 256));
+    int grid = (int)std::min<int64_t>((int64_t)c->num_sms * 8, div_ceil(c->here, 256));
     verify_kernel<<<grid, 256, 0, c->stream>>>(c->buf[c->cur], c->here, c->small + 40);
     CU(c, cudaGetLastError());
   }

@@ -26,9 +26,8 @@ LSB_MAX_SUBPASSES = 32
 LSB_COMM_ID_BYTES = 128
 FLAG_PHASE_EVENTS = 1
 FLAG_TWO_LEVEL = 2
-FLAG_DIRECT_SCATTER = 4
+FLAG_TWO_STEP = 4
 FLAG_NO_SKIP = 8
-FLAG_NO_PIPELINE = 16
 
 
 class LsbError(RuntimeError):
@@ -89,6 +88,7 @@ def load_library():
     L.lsb_last_error.restype = ctypes.c_char_p
     L.lsb_status_string.argtypes = [ci]
     L.lsb_status_string.restype = ctypes.c_char_p
+    L.lsb_tune.argtypes = [ctypes.c_char_p, ci]
     L.lsb_comm_unique_id.argtypes = [vp]
     L.lsb_comm_init.argtypes = [vp, vp]
     L.lsb_barrier.argtypes = [vp]
@@ -119,18 +119,15 @@ def abi_symbols():
     return [s for s in header_symbols() if hasattr(L, s)]
 
 
-def _prefer_torch_nccl():
-    """liblsbsort binds whichever libnccl.so.2 the process already has; make that PyTorch's
-    bundled one when PyTorch is installed, so both agree on a single NCCL."""
-    try:
-        import torch  # noqa: F401
-    except ImportError:
-        pass
+def tune(key, value):
+    """experiment knob for profiling sweeps (lsb_tune): applies to sorters created afterwards"""
+    rc = load_library().lsb_tune(key.encode(), int(value))
+    if rc:
+        raise LsbError(rc, "lsb_tune", load_library().lsb_last_error(None).decode())
 
 
 def comm_unique_id():
     """MPI_Init's rendezvous token: rank 0 makes it, every rank passes it to comm_init"""
-    _prefer_torch_nccl()
     buf = ctypes.create_string_buffer(LSB_COMM_ID_BYTES)
     rc = load_library().lsb_comm_unique_id(buf)
     if rc:
@@ -200,8 +197,7 @@ class DistributedSorter:
             pass
 
     def comm_init(self, unique_id):
-        _prefer_torch_nccl()
-        self._check(self._L.lsb_comm_init(self._ctx, unique_id), "lsb_comm_init")
+            self._check(self._L.lsb_comm_init(self._ctx, unique_id), "lsb_comm_init")
 
     def barrier(self):
         """MPI_Barrier(MPI_COMM_WORLD): all GPUs drained their sort streams"""

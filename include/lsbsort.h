@@ -39,6 +39,7 @@ extern "C" {
 #define LSB_ABI_VERSION 1
 #define LSB_MAX_GPUS 8
 #define LSB_MAX_SUBPASSES 32
+#define LSB_MAX_PARTS 16   /* parts per shard of the multi-GPU pass (virtual ranks) */
 #define LSB_COMM_ID_BYTES 128
 
 typedef enum {
@@ -81,24 +82,23 @@ typedef struct lsb_config {
 
 #define LSB_FLAG_NONE 0u
 #define LSB_FLAG_PHASE_EVENTS 1u /* record a CUDA event after every kernel of lsb_sort      */
-#define LSB_FLAG_DIRECT_SCATTER 4u /* G > 1: let the scatter kernel store its 20-element runs
-                                      directly into the peers (no separate exchange kernel); faster
-                                      below ~2^28 elements per GPU, slower above  */
-#define LSB_FLAG_NO_SKIP 8u       /* do not skip sub-passes whose digit is constant over the shard
+#define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (virtual ranks: per-part counts,
+                                    digit-major / rank-minor scan, part sort + exchange kernel)
+                                    even when world_size == 1                                  */
+#define LSB_FLAG_TWO_STEP 4u     /* sort a 9..16-bit digit as two stable 8-bit counting-sort steps
+                                    over HBM (round 1's shape, 64 B/element/pass) instead of the
+                                    one-pass kernel (32 B/element/pass); same permutation       */
+#define LSB_FLAG_NO_SKIP 8u      /* do not skip passes whose digit is constant over the shard
                                     (a stable pass on a constant digit is the identity; the
                                     reference always runs it; chpl passes nBits for the same
                                     purpose, chpl/arkouda-radix-sort.chpl:70,78)              */
-#define LSB_FLAG_NO_PIPELINE 16u  /* G > 1: sort the whole shard, then exchange it (no overlap of the
-                                    NVLink time with the local sort of the next part)          */
-#define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (segment count + global scan +
-                                    segmented scatter) even when world_size == 1            */
 
 /* what lsb_sort / lsb_pass measured, device time from CUDA events on the sort stream */
 typedef struct lsb_stats {
   double device_ms;       /* whole call: first kernel start -> last kernel end             */
   int32_t passes;         /* reference passes run (N_DIGITS, :22)                          */
-  int32_t subpasses;      /* partition-kernel launches (2 per 16-bit pass)                 */
-  int32_t skipped;        /* sub-passes skipped because their digit was constant           */
+  int32_t subpasses;      /* scatter-kernel launches (1 per pass and part; 2 with TWO_STEP) */
+  int32_t skipped;        /* passes skipped because their digit was constant               */
   int32_t reserved0;
   int64_t elements;       /* elements of THIS shard that took part                         */
   double hist_ms;         /* count kernels (needs LSB_FLAG_PHASE_EVENTS, else 0)           */
@@ -130,6 +130,14 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg);
 void lsb_destroy(lsb_ctx* ctx);
 const char* lsb_last_error(const lsb_ctx* ctx);
 const char* lsb_status_string(int status);
+
+/* Experiment knob (profiling sweeps only; the defaults are what bench.py measures): sets a
+ * process-wide tunable read by the NEXT lsb_create.  Keys: "op_t1" (tiles per supertile of
+ * the one-pass kernel, 1..256), "op_nx" (supertile scratch buffers), "op_lead", "op_hints"
+ * (L2 eviction hints, bit mask), "op_ctas_mgpu" (one-pass CTAs per SM while an exchange kernel
+ * shares the GPU), "vparts" (parts per shard, G > 1), "ex_ctas" (exchange CTAs per SM),
+ * "timeout_ms" (watchdog of the one-pass kernel).  Unknown key / bad value: LSB_ERR_ARG. */
+int lsb_tune(const char* key, int value);
 
 /* ---- multi-GPU wiring (MPI_Init / MPI_COMM_WORLD, :588,:613-616) ----------------- */
 

@@ -34,7 +34,7 @@ def test_generate_matches_oracle(n, R, mask, k):
 
 @pytest.mark.parametrize("n,R", [(0, 1), (1, 1), (1, 4), (3, 4), (7, 3), (10, 8), (100, 4), (4095, 2), (4096, 1),
                                  (4097, 2), (65536, 4), (65537, 4), (1 << 20, 4), ((1 << 21) + 12345, 8)])
-@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL, L.FLAG_TWO_STEP])
 def test_sort_matches_oracle(n, R, flags):
     with lsb.DistributedSorter(n, ranks=R, flags=flags) as s:
         s.generate()
@@ -101,7 +101,7 @@ def test_each_pass_matches_reference_pass(golden_dir, bits, flags):
 
 
 @pytest.mark.parametrize("mask,k", [(0xFFFFFF, 1), (ALL, 3), (0xFF, 1), (0, 1), (0xFFFF0000FFFF, 2)])
-@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+@pytest.mark.parametrize("flags", [0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL])
 def test_skewed_keys_stable(mask, k, flags):
     # config 4: single-bin digits, massive ties; stability decides the answer
     n, R = 700001, 4
@@ -118,21 +118,61 @@ def test_skewed_keys_stable(mask, k, flags):
 
 
 def test_constant_digits_are_skipped_not_missorted():
-    # 24-bit keys: sub-digits 3..7 are constant -> 5 of the 8 launches are skipped, same bytes out
+    # 24-bit keys: digits 2 and 3 are constant -> 2 of the 4 passes are skipped, same bytes out
     n, R = 300000, 2
     g = O.generate(n, R, key_mask=0xFFFFFF)
     want = O.sort(g, n, R)
-    for flags, skipped in ((0, 5), (L.FLAG_NO_SKIP, 0)):
+    for flags, skipped in ((0, 2), (L.FLAG_NO_SKIP, 0)):
         with lsb.DistributedSorter(n, ranks=R, key_mask=0xFFFFFF, flags=flags) as s:
             s.generate()
             st = s.my_sort()
-            assert st.skipped == skipped and st.subpasses == 8 - skipped and st.passes == 4
+            assert st.skipped == skipped and st.subpasses == 4 - skipped and st.passes == 4
             assert (s.download() == want).all()
     with lsb.DistributedSorter(1000, key_mask=0) as s:  # every digit constant: nothing to do at all
         s.generate()
         st = s.my_sort()
-        assert st.subpasses == 0 and st.skipped == 8
+        assert st.subpasses == 0 and st.skipped == 4
         assert (s.download() == O.generate(1000, 1, key_mask=0)[:1000]).all()
+
+
+@pytest.mark.parametrize("t1,nx", [(1, 2), (3, 3), (7, 4)])
+@pytest.mark.parametrize("mask,k,bits", [(ALL, 1, 16), (0xFFFFFF, 1, 16), (ALL, 4, 16), (ALL, 1, 11), (0xF0F0F0F0F0F0F0F0, 2, 13)])
+def test_onepass_many_small_supertiles(t1, nx, mask, k, bits):
+    """the one-pass kernel with supertiles of 1-7 tiles: scratch-ring reuse, frontier versions across
+    dozens of supertiles, segments cut into sub-tiles with look-back (skew), short last supertile"""
+    n, R = 250007, 3
+    g = O.generate(n, R, key_mask=mask, and_draws=k)
+    want = O.sort(g, n, R, bits)
+    lsb.tune("op_t1", t1)
+    lsb.tune("op_nx", nx)
+    try:
+        with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, key_mask=mask, and_draws=k, flags=L.FLAG_NO_SKIP) as s:
+            s.generate()
+            s.my_sort()
+            assert (s.download() == want).all()
+    finally:
+        lsb.tune("op_t1", 238)
+        lsb.tune("op_nx", 3)
+
+
+def test_grouped_upper_bits_large_ragged_n():
+    """keys whose upper 32 bits are constant over long stretches (whole warps agree on a digit), n > 1M
+    and n % 32 != 0: the warp-aggregated count path and the tail chunk of the count kernel"""
+    n = (1 << 20) + 300000 + 13
+    rng = np.random.default_rng(11)
+    a = np.zeros(n, dtype=lsb.ELT)
+    hi = np.repeat(rng.integers(0, 5, n // 4096 + 1, dtype=np.uint64), 4096)[:n]
+    a["key"] = (hi << np.uint64(32)) | rng.integers(0, 1 << 32, n, dtype=np.uint64)
+    a["val"] = np.arange(n, dtype=np.uint64)
+    want = O.stable_sort(a, n)
+    for flags in (0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL):
+        with lsb.DistributedSorter(n, flags=flags) as s:
+            s.upload(a)
+            for p in range(4):
+                c = s.histogram(p)
+                assert c.sum() == n and (c == np.bincount((a["key"] >> np.uint64(16 * p)).astype(np.int64) & 0xFFFF, minlength=65536)).all()
+            s.my_sort()
+            assert (s.download() == want).all()
 
 
 def test_uploaded_data_and_host_path():
@@ -197,7 +237,7 @@ def test_large_properties(n):
         # idempotence: sorting sorted data changes nothing
         s.my_sort()
         assert list(s.verify().checksum) == before
-    assert st.subpasses == 8
+    assert st.subpasses == 4
 
 
 def test_errors_are_reported_not_swallowed():
@@ -267,8 +307,7 @@ def test_randomised_parity_sweep():
         bits = int(rng.choice([1, 3, 5, 7, 8, 9, 10, 11, 12, 14, 15, 16])) if case % 3 == 0 else 16
         mask = masks[int(rng.integers(0, len(masks)))]
         k = int(rng.integers(1, 4))
-        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_DIRECT_SCATTER,
-                 L.FLAG_TWO_LEVEL | L.FLAG_NO_PIPELINE][case % 5]
+        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_TWO_STEP, L.FLAG_TWO_STEP][case % 5]
         if bits < 4 and n > 20000:
             n = 20000  # 64 passes of a 1-bit digit: keep the oracle quick
         g = O.generate(n, R, key_mask=mask, and_draws=k)
