@@ -8,6 +8,10 @@
 A "step" is one full mySort (all passes) over one freshly generated synthetic input.
   N = 1 : BASELINE configs[1] -- single B200, n = 2^30 uniform pcg64 keys, 16-bit digits.
   N > 1 : BASELINE configs[2] weak scaling -- 2^31 elements per GPU, R = N pcg64 streams.
+  --strong        configs[2] strong scaling: n = 2^33 in total at N = 4/8, 2^32 at N = 1/2 (2^33 does not fit)
+  --key-mask / --and-draws   configs[3] skewed keys;  --radix 8|11|16   configs[4] digit-width sweep
+Constant-digit passes are NOT skipped in the measured line (the reference always runs them); a skewed
+run also reports the skipping variant as `skip_variant`.
 `value` is device time (CUDA events on the sort stream, inputs already in HBM, max over ranks);
 `e2e` is the same metric through the host-buffer C-ABI call lsb_sort_host (pinned host memory
 in, pinned host memory out, copies inside the timed region, wall clock).
@@ -27,6 +31,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "M 16-byte elements sorted/s"
+ALL_BITS = 0xFFFFFFFFFFFFFFFF
 UNIT = "M elements/s"
 
 
@@ -109,11 +114,30 @@ def cpu_baseline(sample_log2=None):
                       f"{ranks} ranks, n=2^{n.bit_length() - 1} --no-verify, {secs:.2f} s sort time"}
 
 
+def bench_shape(args, world):
+    """(elements per GPU as log2, n total, scaling) of the workload both arms report"""
+    if args.strong:
+        total_log2 = args.strong_log2 or (33 if world >= 4 else 32)
+        per = total_log2 - (world.bit_length() - 1)
+        return per, 1 << total_log2, "strong"
+    per = args.log2n if args.log2n else (30 if world == 1 else 31)
+    return per, world << per, "weak"
+
+
+def config_dict(args, world, n, here, npass):
+    return {"workload": workload_name(world, args), "n_total": n, "n_per_gpu": here, "radix_bits": args.radix,
+            "passes": npass, "pcg_streams": world, "key_mask": hex(args.key_mask), "and_draws": args.and_draws,
+            "skip_constant_digits": False,
+            "l2": "inputs (16-64 GiB per GPU) are far larger than the 126 MB L2; no flush needed"}
+
+
 def main_reference(args, rank):
     if rank != 0:
         return 0
+    world = args.gpus
     cores = host_threads()
     ranks = max(1, min(cores, 64))
+    per_log2, n_total, scaling = bench_shape(args, world)
     n = 1 << args.ref_log2
     for _ in range(args.warmup and 1):
         run_reference_once(n, ranks)
@@ -123,15 +147,16 @@ def main_reference(args, rank):
         rates.append(r)
         secs.append(s)
     value = n * len(secs) / sum(secs) / 1e6
+    npass = -(-64 // args.radix)
+    sample = (f"unmodified mpi/mpi_lsbsort.cpp via oracle/_ref (ranks-as-threads mpi.h shim, no MPI on the box), {ranks} ranks "
+              f"on {cores} host threads, each step = a 2^{args.ref_log2}-element sample of the workload, --no-verify, uniform keys, "
+              f"16-bit digits (the reference has neither a skew nor a radix knob)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus), "sample": f"n=2^{args.ref_log2} per step on the host CPU",
-                   "radix_bits": 16},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ranks, "kind": "reference",
-                         "sample": f"unmodified mpi/mpi_lsbsort.cpp via oracle/_ref (shim transport), {ranks} ranks, "
-                                   f"n=2^{args.ref_log2} --no-verify per step"},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": config_dict(args, world, n_total, n_total // world, npass),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ranks, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -139,10 +164,20 @@ def main_reference(args, rank):
     return 0
 
 
-def workload_name(gpus):
+def workload_name(gpus, args):
+    per_log2, n, scaling = bench_shape(args, gpus)
+    keys = "uniform-random"
+    if args.key_mask != ALL_BITS or args.and_draws > 1:
+        keys = f"skewed (configs[3]: key = AND of {args.and_draws} pcg64 draws & {hex(args.key_mask)})"
+    npass = -(-64 // args.radix)
+    what = f"{keys} 16-byte elements, {args.radix}-bit digits ({npass} passes)"
+    if scaling == "strong":
+        return f"configs[2] strong scaling: {gpus}xB200, 2^{n.bit_length() - 1} elements in total, {what}"
     if gpus == 1:
-        return "configs[1]: single B200, 2^30 uniform-random 16-byte elements, 16-bit digits (4 passes)"
-    return f"configs[2] weak scaling: {gpus}xB200, 2^31 16-byte elements per GPU, 16-bit digits (4 passes)"
+        tag = "configs[1]" if (per_log2 == 30 and args.radix == 16 and keys == "uniform-random") else "single-GPU point"
+        return f"{tag}: single B200, 2^{per_log2} {what}"
+    tag = "configs[4] digit-width sweep" if args.radix != 16 else "configs[2] weak scaling"
+    return f"{tag}: {gpus}xB200, 2^{per_log2} elements per GPU, {what}"
 
 
 # --------------------------------------------------------------------------------------
@@ -172,11 +207,15 @@ def main_cuda(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    per_gpu_log2 = args.log2n if args.log2n else (30 if world == 1 else 31)
-    n = world << per_gpu_log2
-    def make_sorter(n_total, flags):
+    per_gpu_log2, n, scaling = bench_shape(args, world)
+    for kv in args.tune:
+        k_, v_ = kv.split("=")
+        lsb.tune(k_, int(v_))
+
+    def make_sorter(n_total, flags, skip=False):
         s_ = lsb.DistributedSorter(n_total, ranks=world, world_size=world, world_rank=rank, device=local_rank,
-                                   radix_bits=args.radix, flags=flags)
+                                   radix_bits=args.radix, key_mask=args.key_mask, and_draws=args.and_draws,
+                                   flags=flags | (0 if skip else L.FLAG_NO_SKIP))
         if world > 1:
             ids = [lsb.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -186,14 +225,18 @@ def main_cuda(args, rank, world, local_rank):
     sorter = make_sorter(n, L.FLAG_PHASE_EVENTS if args.phases else 0)
 
     # ---- warm-up (also the correctness gate: a wrong sort is not a benchmark) ----
+    # mpi/mpi_lsbsort.cpp:722-736: the output must be the stable sort of the input.  On every rank:
+    # (key,val) strictly increasing within and across shards, n elements, and the GLOBAL multiset
+    # hash (all-gathered by lsb_verify_device) unchanged by the sort -- for any world size.
     for w in range(args.warmup):
         sorter.generate()
-        before = sorter.checksum() if w == 0 else None
+        before = sorter.verify(raise_on_failure=False) if w == 0 else None
         sorter.my_sort()
         if w == 0:
             v = sorter.verify()
-            if world == 1 and list(v.checksum) != before:
-                raise SystemExit("bench.py: multiset hash changed across the sort")
+            if list(v.checksum) != list(before.checksum) or v.elements != n or before.elements != n:
+                raise SystemExit(f"bench.py: rank {rank}: the sort changed the multiset of elements "
+                                 f"({v.elements} of {n} elements, hash {list(v.checksum)} vs {list(before.checksum)})")
 
     # ---- timed: exactly K steps, device time per step, max over ranks ----
     sampler = ClockSampler(local_rank)
@@ -215,6 +258,21 @@ def main_cuda(args, rank, world, local_rank):
 
     # ---- per-kernel durations for the roofline (phase events; separate, untimed-for-value step) ----
     sorter.close()
+    skip_variant = None
+    if args.key_mask != ALL_BITS or args.and_draws > 1:  # the same workload with constant-digit passes skipped
+        sk = make_sorter(n, 0, skip=True)
+        sk_ms, sk_skipped = [], 0
+        for i in range(1 + min(args.steps, 3)):
+            sk.generate()
+            barrier()
+            st = sk.my_sort()
+            barrier()
+            if i:
+                sk_ms.append(max_over_ranks(st.device_ms))
+            sk_skipped = st.skipped
+        sk.close()
+        skip_variant = {"value": n / (statistics.mean(sk_ms) / 1e3) / 1e6, "unit": UNIT, "ms_per_step": statistics.mean(sk_ms),
+                        "passes_skipped": sk_skipped}
     sorter = make_sorter(n, L.FLAG_PHASE_EVENTS)
     kp_ms, kp_n, hist_ms = [], 0, []
     for _ in range(max(2, min(args.steps, 3))):
@@ -223,8 +281,9 @@ def main_cuda(args, rank, world, local_rank):
         st = sorter.my_sort()
         kp_ms.append(st.partition_ms / max(st.partition_launches, 1))
         kp_n = st.partition_launches
-        kp_elems = st.partition_elements / max(st.partition_launches, 1)  # elements per launch (a part when pipelined)
+        kp_elems = st.partition_elements / max(st.partition_launches, 1)  # elements per launch (a part when G > 1)
         hist_ms.append(st.hist_ms)
+        exch_ms = st.exchange_ms
     peak, peak_src = _peaks()
     here = sorter.here
     launch_ms = statistics.mean(kp_ms)
@@ -239,8 +298,11 @@ def main_cuda(args, rank, world, local_rank):
     pass_bound = "hbm" if here * 32 / (peak * 1e9) >= here * 16 * f_remote / (nvlink_gbs * 1e9) else "nvlink"
     pass_frac = t_pass_min * npass / sort_ms
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
-    if os.path.exists(tp):
+    kernel_name = "lsb::onepass_kernel (one stable scatter on a 16-bit digit = one reference pass over its input)"
+    if args.radix <= 8:
+        kernel_name = "lsb::partition_kernel (one stable scatter on a digit of <= 8 bits = one reference pass)"
+    tp = os.path.join(ROOT, "profiles", "onepass_traffic.json")
+    if os.path.exists(tp) and args.radix > 8:
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_element", 0) * kp_elems or None  # per launch
 
@@ -296,30 +358,33 @@ def main_cuda(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sort_ms, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": sort_ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(world), "n_total": n, "n_per_gpu": here, "radix_bits": args.radix,
-                       "passes": npass, "pcg_streams": world,
-                       "l2": "inputs (16-32 GiB per GPU) are far larger than the 126 MB L2; no flush needed"},
+            "config": config_dict(args, world, n, here, npass),
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "lsb::partition_kernel (one 8-bit stable counting-sort step)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": kp_elems * 32, "launch_ms": launch_ms,
-                         "launches_per_sort": kp_n,
-                         "note": "a launch reads and writes every 16-byte element once (32 B/elem); a 16-bit "
-                                 "reference pass takes two launches, see pass_roofline"},
-            "pass_roofline": {"bound": pass_bound, "t_pass_min_ms": t_pass_min, "t_pass_ms": sort_ms / npass,
-                              "frac": pass_frac, "f_remote": f_remote, "hbm_gbs": peak, "nvlink_gbs": nvlink_gbs,
-                              "algorithmic_bytes_per_pass_hbm": here * 32,
-                              "algorithmic_bytes_per_pass_nvlink": here * 16 * f_remote,
-                              "note": "SURVEY 8(d): slower of 32 B/element of HBM traffic and 16 B x f_remote of "
-                                      "NVLink traffic per reference pass, over the whole sort time (counts, scans, "
-                                      "all partition launches, exchange)"},
+            # frac = (slower of 32 B/element of HBM traffic and 16 B x f_remote of NVLink traffic per
+            # reference pass) / measured time per pass, over the WHOLE sort (counts, scans, scatters, exchange)
+            "roofline": {"bound": pass_bound, "achieved": (here * 32 if pass_bound == "hbm" else here * 16 * f_remote) * npass
+                         / (sort_ms * 1e-3) / 1e9,
+                         "peak": peak if pass_bound == "hbm" else nvlink_gbs, "unit": "GB/s", "frac": pass_frac,
+                         "peak_source": peak_src if pass_bound == "hbm" else "B200_PROFILING.md peer-copy figure (770 GB/s per direction)",
+                         "t_pass_min_ms": t_pass_min, "t_pass_ms": sort_ms / npass, "f_remote": f_remote,
+                         "hbm_gbs": peak, "nvlink_gbs": nvlink_gbs,
+                         "algorithmic_bytes_per_pass_hbm": here * 32,
+                         "algorithmic_bytes_per_pass_nvlink": here * 16 * f_remote,
+                         "kernel": kernel_name, "launch_ms": launch_ms, "launches_per_sort": kp_n,
+                         "algorithmic_bytes_per_launch": kp_elems * 32, "launch_gbs": achieved,
+                         "launch_frac": achieved / peak, "traffic": traffic,
+                         "note": "frac is the per-pass fraction of SURVEY 8(d) over the whole step; launch_frac is the "
+                                 "dominant kernel alone (32 B/element per launch / its CUDA-event duration / HBM peak); "
+                                 "traffic = ncu dram bytes of one launch (profiles/onepass_traffic.json, scaled)"},
             "hist_ms_per_sort": statistics.mean(hist_ms),
+            "exchange_kernel_ms_per_sort": exch_ms,
         }
+        if skip_variant:
+            line["skip_variant"] = skip_variant
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -340,7 +405,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-log2", type=int, default=24, help="--impl reference: log2 of the per-step sample")
+    ap.add_argument("--ref-log2", type=int, default=28, help="--impl reference: log2 of the per-step sample")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: fixed total (2^33 at 4/8 GPUs, 2^32 at 1/2)")
+    ap.add_argument("--strong-log2", type=int, default=0, help="override the fixed total of --strong")
+    ap.add_argument("--key-mask", type=lambda x: int(x, 0), default=ALL_BITS, help="configs[3]: keep only these key bits")
+    ap.add_argument("--and-draws", type=int, default=1, help="configs[3]: key = AND of k pcg64 draws (Zipf-like digits)")
+    ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune (experiments)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

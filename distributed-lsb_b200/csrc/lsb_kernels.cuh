@@ -303,7 +303,7 @@ __device__ __forceinline__ unsigned match_bin(unsigned vmask, unsigned bin) {
 // How a tile of `count` elements is dealt to the warps: rows of 32 elements in contiguous blocks
 // (warp order == index order, which the stable per-warp offsets need), as evenly as the count
 // allows, so a partly filled tile keeps every warp busy.  Only the last row of a tile can be
-// partial; it belongs to one warp and is handled outside the unrolled loop over full rows.
+// partial; it belongs to the last warp that has rows and is handled outside the unrolled loop.
 struct RowPlan {
   int row0;      // first row of this warp
   int nfull;     // full rows of this warp
@@ -314,41 +314,66 @@ __device__ __forceinline__ RowPlan row_plan(int count) {
   const int warp = threadIdx.x >> 5;
   const int full = count >> 5, tail = count & 31;
   const int rows = full + (tail ? 1 : 0);
-  const int rpw = (rows + C::WARPS - 1) / C::WARPS;
+  const int base = rows / C::WARPS, extra = rows % C::WARPS;  // WARPS is a power of two
   RowPlan r;
-  r.row0 = warp * rpw;
-  const int mine = max(0, min(rpw, rows - r.row0));
+  r.row0 = warp * base + min(warp, extra);
+  const int mine = base + (warp < extra ? 1 : 0);
   r.nfull = max(0, min(mine, full - r.row0));
   r.ptail = (mine > r.nfull) ? tail : 0;
   return r;
 }
 
-// bins of my elements + per-warp 256-bin counts (packed u16, shared atomics)
-template <class C>
-__device__ __forceinline__ void op_count(const Elt* s_raw, const RowPlan& rp, int shift, unsigned mask,
-                                         unsigned short* s_whist, unsigned (&bins)[C::IPT], unsigned& bin_p) {
+// 8-bit digit of an element in shared memory; BYTE: the digit is exactly byte `shift / 8` of the key
+template <bool BYTE>
+__device__ __forceinline__ unsigned tile_bin(const Elt* e, int shift, unsigned mask) {
+  if (BYTE) return reinterpret_cast<const unsigned char*>(e)[shift >> 3];
+  return (unsigned)(e->key >> shift) & mask;
+}
+
+// Stable ranks, step 1: every element's rank among the elements of its bin that precede it IN ITS
+// WARP's rows (8 ballots per row find the peers; a per-warp counter per bin runs over the rows).
+// On return info[j] = bin | rank << 8 for row j, and the warp's counters hold its counts per bin --
+// no separate counting pass over the tile.  s_whist must be zero on entry.
+template <class C, bool FULL, bool BYTE>
+__device__ __forceinline__ void op_rank(const Elt* __restrict__ s_raw, const RowPlan& rp, int shift, unsigned mask,
+                                        unsigned short* __restrict__ s_whist, unsigned (&info)[C::IPT], unsigned& info_p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
-  const Elt* row = s_raw + rp.row0 * 32 + lane;
+  unsigned short* wh = s_whist + warp * 256;
+  const unsigned lt = lanemask_lt();
+  const Elt* row = s_raw + (FULL ? warp * (32 * C::IPT) : rp.row0 * 32) + lane;
+  // all digits first: the loads must not sit inside the serial chain of counter updates below
+#pragma unroll
+  for (int j = 0; j < C::IPT; j++) info[j] = (FULL || j < rp.nfull) ? tile_bin<BYTE>(row + j * 32, shift, mask) : 0;
+  info_p = (!FULL && lane < rp.ptail) ? tile_bin<BYTE>(row + rp.nfull * 32, shift, mask) : 0;
 #pragma unroll
   for (int j = 0; j < C::IPT; j++) {
-    bins[j] = 0;
-    if (j < rp.nfull) {
-      const unsigned bin = (unsigned)(row[j * 32].key >> shift) & mask;
-      bins[j] = bin;
-      atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
+    if (FULL || j < rp.nfull) {
+      const unsigned bin = info[j];
+      const unsigned peers = match_bin<true>(0xffffffffu, bin);
+      const unsigned old = wh[bin];
+      __syncwarp();
+      if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+      __syncwarp();
+      info[j] = bin | ((old + __popc(peers & lt)) << 8);
     }
   }
-  bin_p = 0;
-  if (lane < rp.ptail) {
-    const unsigned bin = (unsigned)(row[rp.nfull * 32].key >> shift) & mask;
-    bin_p = bin;
-    atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
+  if (!FULL && rp.ptail) {  // warp-uniform
+    const bool valid = lane < rp.ptail;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned bin = info_p;
+      const unsigned peers = match_bin<false>(vmask, bin);
+      const unsigned old = wh[bin];
+      __syncwarp(vmask);
+      if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+      __syncwarp(vmask);
+      info_p = bin | ((old + __popc(peers & lt)) << 8);
+    }
   }
 }
 
-// threads 0..255 only (bin = tid): tile total of the bin, its start inside the sorted tile, and
-// the per-warp running offsets written back over the per-warp counts.  Uses named barrier 1.
+// Step 2, threads 0..255 only (bin = tid): tile total of the bin, its start inside the sorted tile,
+// and each warp's base slot for the bin written back over the warp's count.  Uses named barrier 1.
 template <class C>
 __device__ __forceinline__ void op_scan(unsigned short* s_whist, unsigned* s_wtot, unsigned& tile_count,
                                         unsigned& binstart) {
@@ -378,38 +403,17 @@ __device__ __forceinline__ void op_scan(unsigned short* s_whist, unsigned* s_wto
   }
 }
 
-// stable ranks: slot of each element inside the sorted tile, written as a permutation
-template <class C>
-__device__ __forceinline__ void op_rank(const RowPlan& rp, unsigned short* s_whist, unsigned short* s_perm,
-                                        const unsigned (&bins)[C::IPT], unsigned bin_p) {
+// Step 3: slot = warp base of the bin + rank; the sorted order as a permutation perm[slot] = index
+template <class C, bool FULL>
+__device__ __forceinline__ void op_perm(const RowPlan& rp, const unsigned short* s_whist, unsigned short* s_perm,
+                                        const unsigned (&info)[C::IPT], unsigned info_p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned short* wh = s_whist + warp * 256;
-  const unsigned lt = lanemask_lt();
-  const int idx0 = rp.row0 * 32 + lane;
+  const unsigned short* wh = s_whist + warp * 256;
+  const int idx0 = (FULL ? warp * (32 * C::IPT) : rp.row0 * 32) + lane;
 #pragma unroll
-  for (int j = 0; j < C::IPT; j++) {
-    if (j < rp.nfull) {
-      const unsigned bin = bins[j];
-      const unsigned peers = match_bin<true>(0xffffffffu, bin);
-      const unsigned old = wh[bin];
-      __syncwarp();
-      if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
-      __syncwarp();
-      s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + j * 32);
-    }
-  }
-  if (rp.ptail) {  // warp-uniform
-    const bool valid = lane < rp.ptail;
-    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      const unsigned peers = match_bin<false>(vmask, bin_p);
-      const unsigned old = wh[bin_p];
-      __syncwarp(vmask);
-      if ((peers & lt) == 0) wh[bin_p] = (unsigned short)(old + __popc(peers));
-      __syncwarp(vmask);
-      s_perm[old + __popc(peers & lt)] = (unsigned short)(idx0 + rp.nfull * 32);
-    }
-  }
+  for (int j = 0; j < C::IPT; j++)
+    if (FULL || j < rp.nfull) s_perm[wh[info[j] & 255u] + (info[j] >> 8)] = (unsigned short)(idx0 + j * 32);
+  if (!FULL && lane < rp.ptail) s_perm[wh[info_p & 255u] + (info_p >> 8)] = (unsigned short)(idx0 + rp.nfull * 32);
 }
 
 // ------------------------------------------------------------------------------------
@@ -417,10 +421,10 @@ __device__ __forceinline__ void op_rank(const RowPlan& rp, unsigned short* s_whi
 // (localShuffle's scatter, mpi/mpi_lsbsort.cpp:241-246, for the narrow digits of a radix
 // sweep; wider digits go through onepass_kernel).  One CTA = one tile, taken in input order
 // by a dynamic tile id so that predecessors are always resident:
-//   1. bulk-load the tile; 2. early per-warp counts -> tile totals published for the decoupled
-//   look-back before the ranking starts; 3. stable ranks; 4. look-back over 64-bit {tag, count}
-//   words, 4 predecessor tiles per round trip (the tag is a per-launch generation, so the words
-//   are never cleared); 5. consecutive threads write consecutive slots of a bin's run.
+//   1. bulk-load the tile; 2. stable ranks (which also count); 3. tile totals published for the
+//   decoupled look-back; 4. look-back over 64-bit {tag, count} words, 4 predecessor tiles per round
+//   trip (the tag is a per-launch generation, so the words are never cleared); 5. consecutive
+//   threads write consecutive slots of a bin's run.
 // ------------------------------------------------------------------------------------
 constexpr int PT_LB_WINDOW = 4;
 constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
@@ -468,9 +472,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
   const bool first = tile == 0;
   mbar_wait(&s_bar, 0);
 
-  unsigned bins[C::IPT], bin_p;
+  unsigned info[C::IPT], info_p;
   const RowPlan rp = row_plan<C>(count);
-  op_count<C>(s_raw, rp, a.shift, a.mask, s_whist, bins, bin_p);
+  op_rank<C, false, false>(s_raw, rp, a.shift, a.mask, s_whist, info, info_p);
   __syncthreads();
   unsigned tile_count = 0, binstart = 0;
   uint64_t* my_state = nullptr;
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
     st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
   }
   __syncthreads();
-  op_rank<C>(rp, s_whist, s_perm, bins, bin_p);
+  op_perm<C, false>(rp, s_whist, s_perm, info, info_p);
 
   // decoupled look-back: exclusive prefix of this bin over earlier tiles.  A window of
   // PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles in flight
@@ -536,14 +540,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
 // TLB set conflicts on cross-process peer mappings) when the 22-element runs of the scatter
 // kernel are stored remotely (tools/p2p_bench.cu, tools/p2p_ipc_bench.cu).
 // ------------------------------------------------------------------------------------
-#ifndef LSB_EX_THREADS
-#define LSB_EX_THREADS 512
-#endif
-#ifndef LSB_EX_U
-#define LSB_EX_U 4
-#endif
-constexpr int EX_THREADS = LSB_EX_THREADS;
-constexpr int EX_U = LSB_EX_U;
+constexpr int EX_U = 4;  // 16-byte elements in flight per thread
 
 // ------------------------------------------------------------------------------------
 // Pipelined multi-GPU pass ("virtual ranks"): every shard is cut into V contiguous parts and
@@ -682,6 +679,9 @@ struct ExchVrArgs {
   unsigned* next_dense;    // [G][V][next_nb]
 };
 
+// EX_THREADS = 512 when the exchange has the SMs to itself or shares them with partition_kernel CTAs that
+// come and go; 256 (12.8 K registers) fits beside three resident CTAs of the persistent one-pass kernel.
+template <int EX_THREADS>
 __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArgs a) {
   __shared__ Elt* s_dst[8];
   __shared__ long long s_lim[8];

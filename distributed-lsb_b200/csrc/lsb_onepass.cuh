@@ -104,6 +104,7 @@ struct OnePassArgs {
   unsigned* ticket;     // the one claim counter
   unsigned* done1;      // [nsuper]: K1 tiles finished
   unsigned* done2;      // [nsuper]: sub-tiles of K2(s) that no longer need X[s % NX]
+  unsigned* free2;      // [nsuper]: 1 once X[s % NX] may be overwritten (every gather of K2(s) is done)
   unsigned* ready2;     // [nsuper]: 1 | (nbig << 8) once the schedule of K2(s) is published
   unsigned* limit2;     // [nsuper]: number of sub-tiles of K2(s)
   unsigned* totals;     // [nsuper][256]: elements of segment lo of supertile s
@@ -148,23 +149,50 @@ __device__ __noinline__ bool op_wait_ge(const unsigned* p, unsigned want, const 
 #endif
 constexpr int OP_NPROF = 24;
 
+// K1 tile body after the tile has landed in shared memory: rank by the low byte, publish the
+// pieces, write the tile sorted by low byte into its place in the supertile scratch.
+template <class C, bool FULL, bool BYTE>
+__device__ __forceinline__ void k1_tile(const OnePassArgs& a, const Elt* s_raw, unsigned short* s_perm,
+                                        unsigned short* s_whist, unsigned* s_wtot, int count, int s, int slot, int idx,
+                                        Elt* xo, uint64_t pol_x) {
+  const int tid = threadIdx.x;
+  unsigned info[C::IPT], info_p;
+  const RowPlan rp = FULL ? RowPlan{0, 0, 0} : row_plan<C>(count);
+  op_rank<C, FULL, BYTE>(s_raw, rp, a.shift, 255u, s_whist, info, info_p);
+  __syncthreads();
+  if (tid < 256) {
+    unsigned tile_count, binstart;
+    op_scan<C>(s_whist, s_wtot, tile_count, binstart);
+    st_relaxed_u32(a.oc + ((size_t)(slot * 256 + tid) * a.T1 + idx), (tile_count << 16) | binstart);
+    if (tile_count) atomicAdd(a.totals + (size_t)s * 256 + tid, tile_count);
+  }
+  __syncthreads();
+  op_perm<C, FULL>(rp, s_whist, s_perm, info, info_p);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < C::IPT; k++) {
+    const int p = k * C::THREADS + tid;
+    if (FULL || p < count) st_elt_hint(xo + p, s_raw[s_perm[p]], pol_x);
+  }
+}
+
 // Work items are tickets from ONE counter.  Ticket t -> step t / (T1 + 256): the first T1 tickets
 // of a step are the K1 tiles of supertile `step`, the other 256 are the segments of supertile
 // `step - lead`.  Every dependency of an item points to a smaller ticket, every claimed ticket is
 // held by a running CTA, so the spin-waits below cannot deadlock.
-template <class C>
+template <class C, bool BYTE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OnePassArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
   unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
   unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
-  long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
+  Elt** s_binptr = reinterpret_cast<Elt**>(smem + C::SMEM_BINDST);
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_kind, s_s, s_idx, s_abort, s_j, s_nbig;
+  __shared__ int s_kind, s_s, s_idx, s_abort, s_j, s_nbig, s_count, s_T1s, s_lastg;
   __shared__ unsigned s_wtot[8];
   __shared__ unsigned s_wsum[C::WARPS];
 
-  constexpr int DISP = 32;  // the dispatcher thread (lane 0 of warp 1); thread 0 completes K1 tiles
+  constexpr int DISP = 32;  // the dispatcher thread (lane 0 of warp 1); warp 0 completes K1 tiles
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t S = (int64_t)a.T1 * C::TILE;
   const int ring_rows = a.T1 + 256;
@@ -216,13 +244,12 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
       if (kind == 0) {
         // X[slot] and oc[slot] were last used by supertile s - NX: all its sub-tiles must have
         // finished gathering before this tile overwrites them
-        if (s >= a.NX)
-          ok = op_wait_ge(a.ready2 + (s - a.NX), 1u, a) &&
-               op_wait_ge(a.done2 + (s - a.NX), ld_relaxed_u32(a.limit2 + (s - a.NX)), a);
+        if (s >= a.NX) ok = op_wait_ge(a.free2 + (s - a.NX), 1u, a);
+        const int64_t begin = (int64_t)s * S + (int64_t)idx * C::TILE;
+        const int64_t left = a.m - begin;
+        const unsigned cnt = (unsigned)(left < C::TILE ? left : C::TILE);
+        s_count = (int)cnt;
         if (ok) {
-          const int64_t begin = (int64_t)s * S + (int64_t)idx * C::TILE;
-          const int64_t left = a.m - begin;
-          const unsigned cnt = (unsigned)(left < C::TILE ? left : C::TILE);
           fence_proxy_async();
           mbar_expect_tx(&s_bar, cnt * 16u);
           bulk_load_hint(s_raw, a.src + begin, cnt * 16u, &s_bar, pol_src);
@@ -235,6 +262,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
       s_kind = kind;
       s_s = s;
       s_idx = idx;
+      s_T1s = kind >= 0 ? tiles1(s) : 0;
     }
     for (int i = tid; i < C::WARPS * 128; i += C::THREADS) reinterpret_cast<unsigned*>(s_whist)[i] = 0;
     __syncthreads();
@@ -242,42 +270,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
     const int kind = s_kind, s = s_s, idx = s_idx;
     if (kind < 0) break;
     const int slot = s % a.NX;
-    const int T1s = tiles1(s);
+    const int T1s = s_T1s;
     OP_T(1);  // dispatch
 
     if (kind == 0) {
       // =============================== K1: tile `idx` of supertile s ===============================
-      const int64_t begin = (int64_t)s * S + (int64_t)idx * C::TILE;
-      const int64_t left = a.m - begin;
-      const int count = (int)(left < C::TILE ? left : C::TILE);
+      const int count = s_count;
       mbar_wait(&s_bar, parity);
       parity ^= 1u;
       OP_T(3);  // K1: tile load
-
-      unsigned bins[C::IPT], bin_p;
-      const RowPlan rp = row_plan<C>(count);
-      op_count<C>(s_raw, rp, a.shift, 255u, s_whist, bins, bin_p);
-      __syncthreads();
-      OP_T(4);  // K1: count
-      if (tid < 256) {
-        unsigned tile_count, binstart;
-        op_scan<C>(s_whist, s_wtot, tile_count, binstart);
-        st_relaxed_u32(a.oc + ((size_t)(slot * 256 + tid) * a.T1 + idx), (tile_count << 16) | binstart);
-        if (tile_count) atomicAdd(a.totals + (size_t)s * 256 + tid, tile_count);
-      }
-      __syncthreads();
-      OP_T(5);  // K1: scan
-      op_rank<C>(rp, s_whist, s_perm, bins, bin_p);
-      __syncthreads();
-      OP_T(6);  // K1: rank
       Elt* xo = a.X + (size_t)slot * S + (size_t)idx * C::TILE;
-#pragma unroll
-      for (int k = 0; k < C::IPT; k++) {
-        const int p = k * C::THREADS + tid;
-        if (p < count) st_elt_hint(xo + p, s_raw[s_perm[p]], pol_x);
-      }
+      if (count == C::TILE) k1_tile<C, true, BYTE>(a, s_raw, s_perm, s_whist, s_wtot, count, s, slot, idx, xo, pol_x);
+      else k1_tile<C, false, BYTE>(a, s_raw, s_perm, s_whist, s_wtot, count, s, slot, idx, xo, pol_x);
       __syncthreads();
-      OP_T(7);  // K1: write
+      OP_T(7);  // K1: rank, scan, write
       // completion by warp 0 while the dispatcher already prepares the next item: the tile's X
       // stores become visible (fence) before the tile counts as done; whoever finishes the last
       // tile of the supertile publishes the schedule of K2(s)
@@ -325,7 +331,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
       }
       OP_T(8);  // K1: completion
     } else {
-      // =============================== K2: segment `idx` of supertile s, then help with big ones ===============================
+      // ================ K2: segment `idx` of supertile s, then help with the big segments ================
       const int nbig = s_nbig;
       for (int h = -1; h < nbig; h++) {
         int lo = idx;
@@ -373,7 +379,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
           }
           __syncthreads();
           OP_T(11);  // K2: piece table + scan
-          if (pc) {
+          if (pc) {  // gather: one bulk copy (TMA engine, L2 -> shared) per piece
             int pbeg = (int)(incl - pc);
             for (int i = 0; i < warp; i++) pbeg += (int)s_wsum[i];
             const int cb = max(pbeg, sub_begin), ce = min(pbeg + (int)pc, sub_begin + count);
@@ -386,13 +392,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
             parity ^= 1u;
           }
           OP_T(12);  // K2: gather
-          if (tid == 0) atomicAdd(a.done2 + s, 1u);  // X[slot] is no longer needed by this sub-tile
+          // X[slot] is no longer needed by this sub-tile; the last one of the supertile releases the slot
+          if (tid == 0) s_lastg = atomicAdd(a.done2 + s, 1u) + 1u == ld_relaxed_u32(a.limit2 + s);
 
-          unsigned bins[C::IPT], bin_p;
+          unsigned info[C::IPT], info_p;
           const RowPlan rp = row_plan<C>(count);
-          op_count<C>(s_raw, rp, shift_hi, mask_hi, s_whist, bins, bin_p);
+          op_rank<C, false, BYTE>(s_raw, rp, shift_hi, mask_hi, s_whist, info, info_p);
           __syncthreads();
-          OP_T(13);  // K2: count
+          OP_T(13);  // K2: rank
+          if (s_lastg && tid == 0) st_release_u32(a.free2 + s, 1u);
           if (tid < 256) {
             unsigned tile_count, binstart;
             op_scan<C>(s_whist, s_wtot, tile_count, binstart);
@@ -433,21 +441,20 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
             const uint64_t incl_abs = base + tile_count;
             if (!last) st_relaxed_gpu(my_word, OP_ST_PREFIX | tag | incl_abs);
             else st_relaxed_gpu(fw, ((uint64_t)(s + 1) << 40) | incl_abs);
-            s_bindst[tid] = (long long)base - (long long)binstart;
+            s_binptr[tid] = a.dst + ((long long)base - (long long)binstart);
           }
           __syncthreads();
           if (s_abort) break;
           OP_T(14);  // K2: scan + frontier
-          op_rank<C>(rp, s_whist, s_perm, bins, bin_p);
+          op_perm<C, false>(rp, s_whist, s_perm, info, info_p);
           __syncthreads();
-          OP_T(15);  // K2: rank
+          OP_T(15);  // K2: permutation
 #pragma unroll
           for (int k = 0; k < C::IPT; k++) {
             const int p = k * C::THREADS + tid;
             if (p < count) {
               const Elt el = s_raw[s_perm[p]];
-              const unsigned bin = (unsigned)(el.key >> shift_hi) & mask_hi;
-              st_elt_hint(a.dst + (s_bindst[bin] + p), el, pol_dst);
+              st_elt_hint(s_binptr[(unsigned)(el.key >> shift_hi) & mask_hi] + p, el, pol_dst);
             }
           }
           OP_T(20);  // K2: scatter

@@ -53,15 +53,16 @@ struct PassPlan {
 
 // process-wide tunables read by lsb_create (lsb_tune); defaults are what bench.py measures
 struct Tuning {
-  int op_cfg = 0;        // one-pass tile shape: 0 = 512 threads x 11 (2 CTAs/SM), 1 = 256 x 11 (4 CTAs/SM)
+  int op_cfg = 1;        // one-pass tile shape: 0 = 512 threads x 11 (2 CTAs/SM), 1 = 256 x 11 (4 CTAs/SM)
   int op_persist = 0;    // MiB of L2 set aside for persisting (evict_last) lines, 0 = leave the device default
-  int op_t1 = 238;       // K1 tiles per supertile of the one-pass kernel (<= 256)
-  int op_nx = 3;         // supertile scratch buffers
-  int op_lead = 1;       // K1 phases claimed ahead of the matching K2 phase
-  int op_hints = 7;      // L2 eviction hints, see OnePassArgs::hints
-  int op_ctas_mgpu = 1;  // one-pass CTAs per SM while an exchange kernel shares the GPU (G > 1)
+  int op_t1 = 232;       // K1 tiles per supertile of the one-pass kernel (<= 256): segments of ~2550 elements
+  int op_nx = 6;         // supertile scratch buffers
+  int op_lead = 3;       // K2(s) is claimed after K1(s + lead): ~2 waves of tickets between a tile and its use
+  int op_hints = 15;     // L2 eviction hints, see OnePassArgs::hints
+  int op_ctas_mgpu = 3;  // one-pass CTAs per SM while an exchange kernel shares the GPU (G > 1)
   int vparts = 8;        // parts per shard of the multi-GPU pass
   int ex_ctas = 1;       // exchange CTAs per SM
+  int ex_threads = 256;  // threads per exchange CTA (256 or 512)
   int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
 };
 Tuning g_tune;
@@ -391,7 +392,7 @@ int launch_onepass(lsb_ctx* c, const Elt* src, Elt* dst, int64_t m, int shift, i
     // control block layout for this launch (u32 words), then the look-back ring (u64)
     size_t w = 0;
     auto take = [&](size_t n) { size_t o = w; w += n; return o; };
-    const size_t o_ticket = take(4), o_done1 = take(nsuper), o_done2 = take(nsuper), o_ready2 = take(nsuper),
+    const size_t o_ticket = take(4), o_done1 = take(nsuper), o_done2 = take(nsuper), o_free2 = take(nsuper), o_ready2 = take(nsuper),
                  o_limit2 = take(nsuper), o_totals = take(256 * (size_t)nsuper), o_segrow = take(256 * (size_t)nsuper),
                  o_subclaim = take(256 * (size_t)nsuper), o_biglist = take(256 * (size_t)nsuper);
     w = (w + 3) & ~(size_t)3;
@@ -421,6 +422,7 @@ int launch_onepass(lsb_ctx* c, const Elt* src, Elt* dst, int64_t m, int shift, i
     a.ticket = ctl + o_ticket;
     a.done1 = ctl + o_done1;
     a.done2 = ctl + o_done2;
+    a.free2 = ctl + o_free2;
     a.ready2 = ctl + o_ready2;
     a.limit2 = ctl + o_limit2;
     a.totals = ctl + o_totals;
@@ -433,8 +435,14 @@ int launch_onepass(lsb_ctx* c, const Elt* src, Elt* dst, int64_t m, int shift, i
     // every claimed item must belong to a resident CTA: never launch more CTAs than fit
     const int64_t useful = div_ceil(m, c->op_tile) + 256;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)c->num_sms * per_sm, useful));
-    if (c->tune.op_cfg == 1) onepass_kernel<TileCfgS><<<grid, TileCfgS::THREADS, TileCfgS::SMEM, c->stream>>>(a);
-    else onepass_kernel<TileCfg><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+    const bool byte = (shift % 8) == 0 && bits == 16;  // both digit halves are whole bytes of the key
+    if (c->tune.op_cfg == 1) {
+      if (byte) onepass_kernel<TileCfgS, true><<<grid, TileCfgS::THREADS, TileCfgS::SMEM, c->stream>>>(a);
+      else onepass_kernel<TileCfgS, false><<<grid, TileCfgS::THREADS, TileCfgS::SMEM, c->stream>>>(a);
+    } else {
+      if (byte) onepass_kernel<TileCfg, true><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+      else onepass_kernel<TileCfg, false><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+    }
     c->launches += 2;
     CU(c, cudaGetLastError());
   }
@@ -588,8 +596,10 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     x.next_nb = next_nb;
     x.part = c->vpart;
     x.next_dense = c->next_dense;
-    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->tune.ex_ctas, div_ceil(m, (int64_t)EX_THREADS * EX_U));
-    exchange_vr_kernel<<<grid, EX_THREADS, 0, c->xstream>>>(x);
+    const int ex_threads = c->tune.ex_threads == 256 ? 256 : 512;
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->tune.ex_ctas, div_ceil(m, (int64_t)ex_threads * EX_U));
+    if (ex_threads == 256) exchange_vr_kernel<256><<<grid, 256, 0, c->xstream>>>(x);
+    else exchange_vr_kernel<512><<<grid, 512, 0, c->xstream>>>(x);
     c->launches++;
     CU(c, cudaGetLastError());
     if (timed) {
@@ -731,6 +741,7 @@ int lsb_tune(const char* key, int value) {
   else if (k == "op_ctas_mgpu" && value >= 0 && value <= 4) g_tune.op_ctas_mgpu = value;
   else if (k == "vparts" && value >= 1 && value <= LSB_MAX_PARTS) g_tune.vparts = value;
   else if (k == "ex_ctas" && value >= 1 && value <= 8) g_tune.ex_ctas = value;
+  else if (k == "ex_threads" && (value == 256 || value == 512)) g_tune.ex_threads = value;
   else if (k == "timeout_ms" && value >= 1) g_tune.timeout_ms = value;
   else return fail(nullptr, LSB_ERR_ARG, "lsb_tune: unknown key or value out of range: " + k);
   return LSB_OK;
@@ -811,17 +822,21 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   // one-pass kernel: supertile scratch, piece table, control block, frontier table
   CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
   CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
-  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+#define LSB_OP_ATTR(CFG, B)                                                                                       \
+  CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));     \
+  CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  LSB_OP_ATTR(TileCfg, true)
+  LSB_OP_ATTR(TileCfg, false)
+  LSB_OP_ATTR(TileCfgS, true)
+  LSB_OP_ATTR(TileCfgS, false)
+#undef LSB_OP_ATTR
   CUC(cudaFuncSetAttribute(digit_hist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DH_SMEM));
   CUC(cudaFuncSetAttribute(digit_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DH_SMEM));
-  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfgS>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfgS::SMEM));
-  CUC(cudaFuncSetAttribute(onepass_kernel<TileCfgS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   if (c->tune.op_cfg == 1) {
     c->op_tile = TileCfgS::TILE;
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfgS>, TileCfgS::THREADS, TileCfgS::SMEM));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfgS, true>, TileCfgS::THREADS, TileCfgS::SMEM));
   } else {
-    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfg>, TileCfg::THREADS, TileCfg::SMEM));
+    CUC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->op_resident, onepass_kernel<TileCfg, true>, TileCfg::THREADS, TileCfg::SMEM));
   }
   if (c->tune.op_persist > 0) {
     int max_persist = 0;
@@ -838,7 +853,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
     if (c->tune.op_t1 > tiles) c->tune.op_t1 = (int)std::max<int64_t>(1, tiles);
     c->op_S = (int64_t)c->tune.op_t1 * c->op_tile;
     const int64_t nsuper = div_ceil(c->per, c->op_S);
-    const size_t words = 8 + (size_t)nsuper * (4 + 4 * 256);
+    const size_t words = 8 + (size_t)nsuper * (5 + 4 * 256);
     c->op_ctl_bytes = words * 4 + (size_t)c->tune.op_nx * (c->tune.op_t1 + 256) * 256 * sizeof(uint64_t);
     CUC(cudaMalloc(&c->op_ctl, c->op_ctl_bytes));
     CUC(cudaMalloc(&c->op_X, (size_t)c->tune.op_nx * c->op_S * sizeof(Elt)));

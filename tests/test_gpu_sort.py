@@ -135,9 +135,9 @@ def test_constant_digits_are_skipped_not_missorted():
         assert (s.download() == O.generate(1000, 1, key_mask=0)[:1000]).all()
 
 
-@pytest.mark.parametrize("t1,nx", [(1, 2), (3, 3), (7, 4)])
+@pytest.mark.parametrize("t1,nx,lead,cfg", [(1, 2, 1, 1), (3, 3, 1, 0), (7, 4, 2, 1), (5, 6, 3, 1)])
 @pytest.mark.parametrize("mask,k,bits", [(ALL, 1, 16), (0xFFFFFF, 1, 16), (ALL, 4, 16), (ALL, 1, 11), (0xF0F0F0F0F0F0F0F0, 2, 13)])
-def test_onepass_many_small_supertiles(t1, nx, mask, k, bits):
+def test_onepass_many_small_supertiles(t1, nx, lead, cfg, mask, k, bits):
     """the one-pass kernel with supertiles of 1-7 tiles: scratch-ring reuse, frontier versions across
     dozens of supertiles, segments cut into sub-tiles with look-back (skew), short last supertile"""
     n, R = 250007, 3
@@ -145,14 +145,16 @@ def test_onepass_many_small_supertiles(t1, nx, mask, k, bits):
     want = O.sort(g, n, R, bits)
     lsb.tune("op_t1", t1)
     lsb.tune("op_nx", nx)
+    lsb.tune("op_lead", lead)
+    lsb.tune("op_cfg", cfg)
     try:
         with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, key_mask=mask, and_draws=k, flags=L.FLAG_NO_SKIP) as s:
             s.generate()
             s.my_sort()
             assert (s.download() == want).all()
     finally:
-        lsb.tune("op_t1", 238)
-        lsb.tune("op_nx", 3)
+        for key, val in (("op_t1", 232), ("op_nx", 6), ("op_lead", 3), ("op_cfg", 1)):
+            lsb.tune(key, val)
 
 
 def test_grouped_upper_bits_large_ragged_n():

@@ -15,16 +15,19 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=28, help="log2 elements per GPU")
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--radix", type=int, default=16)
-ap.add_argument("--direct", action="store_true")
-ap.add_argument("--no-pipeline", action="store_true")
+ap.add_argument("--two-step", action="store_true")
 ap.add_argument("--mask", type=lambda x: int(x, 0), default=0xFFFFFFFFFFFFFFFF)
+ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune, repeatable")
 a = ap.parse_args()
+for kv in a.tune:
+    k, v = kv.split("=")
+    lsb.tune(k, int(v))
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n = world << a.log2n
 s = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=lr, radix_bits=a.radix,
-                          key_mask=a.mask, flags=L.FLAG_PHASE_EVENTS | (L.FLAG_DIRECT_SCATTER if a.direct else 0) | (L.FLAG_NO_PIPELINE if a.no_pipeline else 0))
+                          key_mask=a.mask, flags=L.FLAG_PHASE_EVENTS | L.FLAG_NO_SKIP | (L.FLAG_TWO_STEP if a.two_step else 0))
 ids = [lsb.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 s.comm_init(ids[0])
@@ -36,14 +39,9 @@ for i in range(a.iters):
     if rank == 0:
         sub = [round(st.subpass_ms[k], 3) for k in range(min(st.subpasses, 32))]
         m = s.here
-        if a.direct:
-            tail = f"global step {m * 16 * (world - 1) / world / (sub[-1] * 1e-3) / 1e9:.0f} GB/s out per GPU"
-        elif st.exchange_ms > 0:
-            tail = (f"exchange {st.exchange_ms:.2f} ms total = "
-                    f"{m * 16 * (world - 1) / world * st.passes / st.exchange_ms / 1e6:.0f} GB/s out per GPU")
-        else:
-            tail = "exchange overlapped with the local sort (pipelined)"
-        print(f"iter {i}: sort {st.device_ms:.2f} ms = {n / st.device_ms / 1e3:.0f} M elem/s; count {st.hist_ms:.2f} ms, "
+        tail = (f"exchange kernels {st.exchange_ms:.2f} ms busy = "
+                f"{m * 16 * (world - 1) / world * st.passes / max(st.exchange_ms, 1e-9) / 1e6:.0f} GB/s out per GPU while running")
+        print(f"[{' '.join(a.tune) or 'default'}{' two-step' if a.two_step else ''}] iter {i}: sort {st.device_ms:.2f} ms = {n / st.device_ms / 1e3:.0f} M elem/s; count {st.hist_ms:.2f} ms, "
               f"scan+coll {st.scan_ms:.2f} ms, partitions {sub} ms; sent {list(st.sent[:world])}; {tail}", flush=True)
 s.close()
 dist.destroy_process_group()

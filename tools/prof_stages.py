@@ -13,9 +13,8 @@ sys.path.insert(0, ROOT)
 import distributed_lsb_b200 as lsb  # noqa: E402
 from distributed_lsb_b200 import lsbsort as L  # noqa: E402
 
-NAMES = {1: "dispatch (claim, slot wait, load issue)", 3: "K1 tile load", 4: "K1 count", 5: "K1 scan", 6: "K1 rank",
-         7: "K1 write", 8: "K1 completion (warp 0)", 11: "K2 piece table", 12: "K2 gather", 13: "K2 count",
-         14: "K2 scan + frontier", 15: "K2 rank", 20: "K2 scatter"}
+NAMES = {1: "dispatch (claim, slot wait, load issue)", 3: "K1 tile load", 7: "K1 rank + scan + write", 8: "K1 completion (warp 0)",
+         11: "K2 piece table", 12: "K2 gather", 13: "K2 rank", 14: "K2 scan + frontier", 15: "K2 permutation", 20: "K2 scatter"}
 ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=28)
 ap.add_argument("--mhz", type=float, default=1965.0)
