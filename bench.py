@@ -127,7 +127,7 @@ def bench_shape(args, world):
 def config_dict(args, world, n, here, npass):
     return {"workload": workload_name(world, args), "n_total": n, "n_per_gpu": here, "radix_bits": args.radix,
             "passes": npass, "pcg_streams": world, "key_mask": hex(args.key_mask), "and_draws": args.and_draws,
-            "skip_constant_digits": False,
+            "skip_constant_digits": False, "one_pass_kernel": bool(args.one_pass),
             "l2": "inputs (16-64 GiB per GPU) are far larger than the 126 MB L2; no flush needed"}
 
 
@@ -212,10 +212,11 @@ def main_cuda(args, rank, world, local_rank):
         k_, v_ = kv.split("=")
         lsb.tune(k_, int(v_))
 
-    def make_sorter(n_total, flags, skip=False):
+    def make_sorter(n_total, flags, skip=False, one_pass=None):
+        one_pass = args.one_pass if one_pass is None else one_pass
         s_ = lsb.DistributedSorter(n_total, ranks=world, world_size=world, world_rank=rank, device=local_rank,
                                    radix_bits=args.radix, key_mask=args.key_mask, and_draws=args.and_draws,
-                                   flags=flags | (0 if skip else L.FLAG_NO_SKIP))
+                                   flags=flags | (0 if skip else L.FLAG_NO_SKIP) | (L.FLAG_ONE_PASS if one_pass else 0))
         if world > 1:
             ids = [lsb.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -273,6 +274,29 @@ def main_cuda(args, rank, world, local_rank):
         sk.close()
         skip_variant = {"value": n / (statistics.mean(sk_ms) / 1e3) / 1e6, "unit": UNIT, "ms_per_step": statistics.mean(sk_ms),
                         "passes_skipped": sk_skipped}
+    alt_path = None
+    if world == 1 and not args.no_alt:  # the other pass shape on the same workload, for the record
+        alt = make_sorter(n, L.FLAG_PHASE_EVENTS, one_pass=not args.one_pass)
+        alt_ms, alt_launch = [], []
+        for i in range(1 + min(args.steps, 3)):
+            alt.generate()
+            before_alt = alt.checksum()
+            st = alt.my_sort()
+            if i == 0 and list(alt.verify().checksum) != before_alt:
+                raise SystemExit("bench.py: alternative pass shape: multiset hash changed across the sort")
+            if i:
+                alt_ms.append(st.device_ms)
+                alt_launch.append(st.partition_ms / max(st.partition_launches, 1))
+        alt.close()
+        tname = "onepass_traffic.json" if not args.one_pass else "partition_traffic.json"
+        tfile = os.path.join(ROOT, "profiles", tname)
+        per_elem = None
+        if os.path.exists(tfile):
+            with open(tfile) as f:
+                per_elem = json.load(f).get("dram_bytes_per_element")
+        alt_path = {"path": "two 8-bit steps per pass (default)" if args.one_pass else "LSB_FLAG_ONE_PASS (one-pass kernel)",
+                    "value": n / (statistics.mean(alt_ms) / 1e3) / 1e6, "unit": UNIT, "ms_per_step": statistics.mean(alt_ms),
+                    "scatter_launch_ms": statistics.mean(alt_launch), "ncu_dram_bytes_per_element_per_launch": per_elem}
     sorter = make_sorter(n, L.FLAG_PHASE_EVENTS)
     kp_ms, kp_n, hist_ms = [], 0, []
     for _ in range(max(2, min(args.steps, 3))):
@@ -298,11 +322,14 @@ def main_cuda(args, rank, world, local_rank):
     pass_bound = "hbm" if here * 32 / (peak * 1e9) >= here * 16 * f_remote / (nvlink_gbs * 1e9) else "nvlink"
     pass_frac = t_pass_min * npass / sort_ms
     traffic = None
-    kernel_name = "lsb::onepass_kernel (one stable scatter on a 16-bit digit = one reference pass over its input)"
-    if args.radix <= 8:
-        kernel_name = "lsb::partition_kernel (one stable scatter on a digit of <= 8 bits = one reference pass)"
-    tp = os.path.join(ROOT, "profiles", "onepass_traffic.json")
-    if os.path.exists(tp) and args.radix > 8:
+    if args.one_pass and args.radix > 8:
+        kernel_name = "lsb::onepass_kernel (one stable scatter on a 9..16-bit digit = one reference pass per launch)"
+        tp = os.path.join(ROOT, "profiles", "onepass_traffic.json")
+    else:
+        kernel_name = ("lsb::partition_kernel (one stable counting-sort step on <= 8 bits; "
+                       + ("two launches" if args.radix > 8 else "one launch") + " per reference pass)")
+        tp = os.path.join(ROOT, "profiles", "partition_traffic.json")
+    if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_element", 0) * kp_elems or None  # per launch
 
@@ -385,6 +412,8 @@ def main_cuda(args, rank, world, local_rank):
         }
         if skip_variant:
             line["skip_variant"] = skip_variant
+        if alt_path:
+            line["alt_path"] = alt_path
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
@@ -411,6 +440,8 @@ def main():
     ap.add_argument("--key-mask", type=lambda x: int(x, 0), default=ALL_BITS, help="configs[3]: keep only these key bits")
     ap.add_argument("--and-draws", type=int, default=1, help="configs[3]: key = AND of k pcg64 draws (Zipf-like digits)")
     ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune (experiments)")
+    ap.add_argument("--one-pass", action="store_true", help="measure LSB_FLAG_ONE_PASS (the one-pass kernel) as the main path")
+    ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other pass shape (N = 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

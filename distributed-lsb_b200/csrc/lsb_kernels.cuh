@@ -145,6 +145,77 @@ __global__ void __launch_bounds__(GEN_THREADS) generate_kernel(const GenArgs a) 
 }
 
 // ------------------------------------------------------------------------------------
+// sub-digit counts for the two-step pass shape (localShuffle's count loop, mpi/mpi_lsbsort.cpp:
+// 226-229, once for the whole sort): ONE read of the shard produces the 256-bin histograms of up to
+// 16 sub-digits.  Block-private shared-memory histograms, coalesced 8-byte key loads with 4 loads in
+// flight per thread, one global atomic per bin per CTA.  NSUB is a compile-time count so the per-key
+// loop is fully unrolled; BYTES = the sub-digits are exactly bytes 0..NSUB-1 of the key (radix 8/16).
+// Skew: when the whole warp agrees on the key's upper 32 bits (keys with few random bits), the
+// sub-digits that live there are counted by one lane (+popc) instead of a 32-way same-address atomic.
+// ------------------------------------------------------------------------------------
+constexpr int HIST_THREADS = 512;
+constexpr int HIST_MAX_SUB = 16;
+
+struct HistArgs {
+  const Elt* src;
+  int64_t m;
+  int32_t nsub;
+  int32_t shift[HIST_MAX_SUB];
+  uint32_t mask[HIST_MAX_SUB];
+  unsigned long long* out;  // [nsub][256], accumulated with atomics (caller zeroes)
+};
+
+template <int NSUB, bool BYTES>
+__device__ __forceinline__ void hist_key(unsigned* sh, uint64_t k, const int* shift, const unsigned* mask,
+                                         unsigned active) {
+  const int leader_lane = __ffs(active) - 1;
+  const unsigned hi = (unsigned)(k >> 32);
+  const bool hi_uniform = __all_sync(active, hi == __shfl_sync(active, hi, leader_lane));
+  const bool leader = (int)(threadIdx.x & 31) == leader_lane;
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) {
+    const int sh_s = BYTES ? 8 * s : shift[s];
+    const unsigned bin = BYTES ? (unsigned)(k >> (8 * s)) & 255u : (unsigned)(k >> sh_s) & mask[s];
+    const bool in_hi = BYTES ? (s >= 4) : (sh_s >= 32);
+    if (in_hi && hi_uniform) {
+      if (leader) atomicAdd(sh + s * 256 + bin, (unsigned)__popc(active));
+    } else {
+      atomicAdd(sh + s * 256 + bin, 1u);
+    }
+  }
+}
+
+template <int NSUB, bool BYTES>
+__global__ void __launch_bounds__(HIST_THREADS) subdigit_hist_kernel(const HistArgs a) {
+  __shared__ unsigned sh[NSUB * 256];
+  for (int i = threadIdx.x; i < NSUB * 256; i += HIST_THREADS) sh[i] = 0;
+  int shift[NSUB];
+  unsigned mask[NSUB];
+#pragma unroll
+  for (int s = 0; s < NSUB; s++) { shift[s] = a.shift[s]; mask[s] = a.mask[s]; }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * HIST_THREADS;  // a multiple of 32
+  int64_t i = (int64_t)blockIdx.x * HIST_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  constexpr int U = 4;
+  // the unrolled loop runs only while the WHOLE warp is in range (full-mask shuffles inside)
+  for (; (i - lane) + 31 + (U - 1) * stride < a.m; i += U * stride) {
+    uint64_t k[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) k[u] = ld_stream_key(a.src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; u++) hist_key<NSUB, BYTES>(sh, k[u], shift, mask, 0xffffffffu);
+  }
+  for (; i < a.m; i += stride) {
+    const unsigned active = __activemask();
+    hist_key<NSUB, BYTES>(sh, ld_stream_key(a.src + i), shift, mask, active);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < NSUB * 256; j += HIST_THREADS)
+    if (sh[j]) atomicAdd(a.out + j, (unsigned long long)sh[j]);
+}
+
+// ------------------------------------------------------------------------------------
 // scans
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
@@ -155,6 +226,21 @@ __device__ __forceinline__ uint64_t warp_incl_scan(uint64_t v) {
     if (lane >= d) v += o;
   }
   return v;
+}
+
+// blockDim.x == 256: exclusive scan of one 256-bin histogram per block.
+// out[b*257 + 0..255] = exclusive prefix, out[b*257 + 256] = total.
+__global__ void __launch_bounds__(256) scan256_kernel(const unsigned long long* hist, int64_t* out) {
+  __shared__ uint64_t wtot[8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const uint64_t c = hist[(size_t)blockIdx.x * 256 + t];
+  const uint64_t incl = warp_incl_scan(c);
+  if (lane == 31) wtot[w] = incl;
+  __syncthreads();
+  uint64_t off = 0;
+  for (int i = 0; i < w; i++) off += wtot[i];
+  out[(size_t)blockIdx.x * 257 + t] = (int64_t)(off + incl - c);
+  if (t == 255) out[(size_t)blockIdx.x * 257 + 256] = (int64_t)(off + incl);
 }
 
 // The reference's copyCountsToGlobalCounts + exclusiveScan + copyStartsFromGlobalStarts
@@ -421,74 +507,121 @@ __device__ __forceinline__ void op_perm(const RowPlan& rp, const unsigned short*
 // (localShuffle's scatter, mpi/mpi_lsbsort.cpp:241-246, for the narrow digits of a radix
 // sweep; wider digits go through onepass_kernel).  One CTA = one tile, taken in input order
 // by a dynamic tile id so that predecessors are always resident:
-//   1. bulk-load the tile; 2. stable ranks (which also count); 3. tile totals published for the
-//   decoupled look-back; 4. look-back over 64-bit {tag, count} words, 4 predecessor tiles per round
-//   trip (the tag is a per-launch generation, so the words are never cleared); 5. consecutive
-//   threads write consecutive slots of a bin's run.
+//   1. bulk-load the tile; 2. early per-warp counts -> tile totals published for the decoupled
+//   look-back before the ranking starts; 3. stable ranks; 4. look-back over 64-bit {tag, count}
+//   words, 4 predecessor tiles per round trip (the tag is a per-launch generation, so the words
+//   are never cleared); 5. consecutive threads write consecutive slots of a bin's run.
 // ------------------------------------------------------------------------------------
 constexpr int PT_LB_WINDOW = 4;
 constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
 
 struct PartArgs {
   const Elt* src;
-  int64_t m;
   int32_t shift;
   uint32_t mask;
-  const int64_t* bases;  // [256]: output index of the first element of each bin
-  uint64_t* lookback;    // [tiles][256]
+  int32_t seg_bits;                // nseg = 1 << seg_bits
+  const int64_t* seg_start;        // [nseg + 1] element offsets into src
+  const uint32_t* seg_tile_start;  // [nseg + 1] tile-index prefix
+  const int64_t* bases;            // [(bin << seg_bits) | seg]: global output index of this shard's
+                                   // first element of (seg, bin)
+  uint64_t* lookback;              // [tiles][256]
   uint32_t* tile_counter;
-  uint64_t tag_agg;      // (2*gen+1) << 56
-  uint64_t tag_inc;      // (2*gen+2) << 56
-  Elt* dst;
+  uint64_t tag_agg;                // (2*gen+1) << 56
+  uint64_t tag_inc;                // (2*gen+2) << 56
+  int64_t per;                     // destination shard size (global index / per = shard)
+  int32_t world;
+  Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
+  // RUNS kernels only: the input is already grouped by the low bits of a wider digit, so the
+  // sorted tile is ordered by that full digit; count its runs into run_counts[digit]
+  unsigned long long* run_counts;
+  int32_t full_shift;
+  uint32_t full_mask;
 };
 
-template <class C>
-__global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
-  extern __shared__ __align__(128) unsigned char smem[];
+// (round 1's kernel, kept as measured: a leaner restatement on the helpers above ran 7 % slower)
+template <class C, bool FULL, bool RUNS>
+__device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
+                                               unsigned* s_wtot, int tile, int seg, int count, bool first,
+                                               int first_tile) {
   Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
   unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
   unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
   long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
-  __shared__ __align__(8) uint64_t s_bar;
-  __shared__ int s_tile;
-  __shared__ unsigned s_wtot[8];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    const int t = (int)atomicAdd(a.tile_counter, 1u);  // grid == number of tiles
-    s_tile = t;
-    const long long begin = (long long)t * C::TILE;
-    const long long left = a.m - begin;
-    const unsigned cnt = (unsigned)(left < C::TILE ? left : C::TILE);
-    mbar_expect_tx(&s_bar, cnt * 16u);
-    bulk_load(s_raw, a.src + begin, cnt * 16u, &s_bar);
+  mbar_wait(s_bar, 0);
+
+  // ---- bins of my elements (warp-striped rows), early per-warp counts ----
+  const int idx0 = warp * (32 * C::IPT) + lane;
+  unsigned bins[C::IPT];
+  unsigned* wh32 = reinterpret_cast<unsigned*>(s_whist + warp * 256);
+#pragma unroll
+  for (int j = 0; j < C::IPT; j++) {
+    const int idx = idx0 + j * 32;
+    bins[j] = 0;
+    if (FULL || idx < count) {
+      const unsigned bin = (unsigned)(s_raw[idx].key >> a.shift) & a.mask;
+      bins[j] = bin;
+      atomicAdd(wh32 + (bin >> 1), 1u << ((bin & 1u) * 16));
+    }
   }
-  for (int i = tid; i < C::WARPS * 128; i += C::THREADS) reinterpret_cast<unsigned*>(s_whist)[i] = 0;
   __syncthreads();
-  const int tile = s_tile;
-  const long long left = a.m - (long long)tile * C::TILE;
-  const int count = (int)(left < C::TILE ? left : C::TILE);
-  const bool first = tile == 0;
-  mbar_wait(&s_bar, 0);
 
-  unsigned info[C::IPT], info_p;
-  const RowPlan rp = row_plan<C>(count);
-  op_rank<C, false, false>(s_raw, rp, a.shift, a.mask, s_whist, info, info_p);
-  __syncthreads();
+  // ---- per bin: tile total (published at once), exclusive over warps, start inside the tile ----
   unsigned tile_count = 0, binstart = 0;
   uint64_t* my_state = nullptr;
   if (tid < 256) {
-    op_scan<C>(s_whist, s_wtot, tile_count, binstart);
     my_state = a.lookback + (size_t)tile * 256 + tid;
+    unsigned wc[C::WARPS];
+#pragma unroll
+    for (int w = 0; w < C::WARPS; w++) {
+      wc[w] = s_whist[w * 256 + tid];
+      tile_count += wc[w];
+    }
     st_relaxed_gpu(my_state, (first ? a.tag_inc : a.tag_agg) | (uint64_t)tile_count);
+    unsigned incl = tile_count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // only the 8 scanning warps
+    binstart = incl - tile_count;
+    for (int i = 0; i < warp; i++) binstart += s_wtot[i];
+    unsigned run = binstart;
+#pragma unroll
+    for (int w = 0; w < C::WARPS; w++) {
+      s_whist[w * 256 + tid] = (unsigned short)run;
+      run += wc[w];
+    }
   }
   __syncthreads();
-  op_perm<C, false>(rp, s_whist, s_perm, info, info_p);
 
-  // decoupled look-back: exclusive prefix of this bin over earlier tiles.  A window of
-  // PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles in flight
-  // the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
+  // ---- stable ranks: slot of each element inside the tile, written as a permutation ----
+  {
+    unsigned short* wh = s_whist + warp * 256;
+    const unsigned lt = lanemask_lt();
+#pragma unroll
+    for (int j = 0; j < C::IPT; j++) {
+      const int idx = idx0 + j * 32;
+      const bool valid = FULL || idx < count;
+      const unsigned vmask = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const unsigned bin = bins[j];
+        const unsigned peers = match_bin<FULL>(vmask, bin);
+        const unsigned old = wh[bin];
+        __syncwarp(vmask);
+        if ((peers & lt) == 0) wh[bin] = (unsigned short)(old + __popc(peers));
+        __syncwarp(vmask);
+        s_perm[old + __popc(peers & lt)] = (unsigned short)idx;
+      }
+    }
+  }
+
+  // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
+  // A window of PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles
+  // in flight the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
   if (tid < 256) {
     uint64_t excl = 0;
     if (!first) {
@@ -499,7 +632,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
 #pragma unroll
         for (int i = 0; i < PT_LB_WINDOW; i++) {
           const int t = look - i;
-          v[i] = (t >= 0) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
+          v[i] = (t >= first_tile) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
         }
         int used = 0;
 #pragma unroll
@@ -515,19 +648,97 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
       }
       st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
     }
-    s_bindst[tid] = a.bases[tid] + (long long)excl - (long long)binstart;
+    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)binstart;
   }
   __syncthreads();
 
+  // ---- write: consecutive threads -> consecutive slots of a bin's run ----
 #pragma unroll
   for (int k = 0; k < C::IPT; k++) {
     const int p = k * C::THREADS + tid;
-    if (p < count) {
-      const Elt el = s_raw[s_perm[p]];
+    const bool valid = FULL || p < count;
+    Elt el;
+    el.key = 0;
+    el.val = 0;
+    if (valid) {
+      el = s_raw[s_perm[p]];
       const unsigned bin = (unsigned)(el.key >> a.shift) & a.mask;
-      st_elt(a.dst + (s_bindst[bin] + p), el);
+      const long long g = s_bindst[bin] + p;
+      Elt* out;
+      if (a.world == 1) {
+        out = a.dst[0] + g;
+      } else {
+        int r = 0;
+        for (int q = 1; q < a.world; q++) r += (g >= (long long)q * a.per);
+        out = a.dst[r] + (g - (long long)r * a.per);
+      }
+      st_elt(out, el);
+    }
+    if (RUNS) {
+      // localShuffle's counts of the FULL digit (:226-229) as a by-product: the sorted tile is
+      // non-decreasing in the full digit, so each warp adds the length of every run it sees
+      const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
+      const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
+      const bool head = valid && (lane == 0 || d != prev);
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      const unsigned nvalid = FULL ? 32u : (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
+      if (head) {
+        const unsigned after = heads & ~((2u << lane) - 1u);
+        const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
+        atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
+      }
     }
   }
+}
+
+template <class C, bool RUNS>
+__global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ int s_tile, s_seg, s_count, s_first, s_first_tile;
+  __shared__ unsigned s_wtot[8];
+
+  const int tid = threadIdx.x;
+  const int nseg = 1 << a.seg_bits;
+
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    const unsigned t = atomicAdd(a.tile_counter, 1u);
+    s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
+    s_seg = 0;
+  }
+  // zero the packed per-warp histograms (WARPS*256 u16)
+  for (int i = tid; i < C::WARPS * 128; i += C::THREADS)
+    reinterpret_cast<unsigned*>(smem + C::SMEM_WHIST)[i] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile < 0) return;
+  // which segment owns this tile: the one with first_tile <= tile < next first_tile
+  if (nseg > 1) {
+    if (tid < nseg) {
+      const unsigned f = a.seg_tile_start[tid], l = a.seg_tile_start[tid + 1];
+      if (f <= (unsigned)tile && (unsigned)tile < l) s_seg = tid;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int sg = s_seg;
+    const unsigned t_in = (unsigned)tile - a.seg_tile_start[sg];
+    const long long begin = a.seg_start[sg] + (long long)t_in * C::TILE;
+    const long long left = a.seg_start[sg + 1] - begin;
+    const int cnt = (int)(left < C::TILE ? left : C::TILE);
+    s_count = cnt;
+    s_first = (t_in == 0);
+    s_first_tile = (int)a.seg_tile_start[sg];
+    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
+    bulk_load(smem + C::SMEM_RAW, a.src + begin, (unsigned)cnt * 16u, &s_bar);
+  }
+  __syncthreads();
+  const int count = s_count;
+  if (count == C::TILE)
+    partition_tile<C, true, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+  else
+    partition_tile<C, false, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
 }
 
 // ------------------------------------------------------------------------------------

@@ -4,9 +4,11 @@
 // Host-side restatement of the reference's pass structure, mpi/mpi_lsbsort.cpp:481-585
 // (globalShuffle / mySort), for device-resident shards.
 //
-//   G == 1 : ONE read of the shard counts the digits of every pass (digit_hist_kernel); each pass
-//            is then one launch that moves every element through HBM once: onepass_kernel for
-//            digits of 9..16 bits (the reference's 16), partition_kernel for digits of <= 8 bits.
+//   G == 1 : ONE read of the shard counts every (sub-)digit of the sort; then, per reference pass,
+//            default: two stable 8-bit counting-sort steps over HBM (low bits, then high bits --
+//              the same permutation as one stable step on the full digit), partition_kernel;
+//            LSB_FLAG_ONE_PASS: ONE launch that moves every element through HBM once
+//              (onepass_kernel, lsb_onepass.cuh) for digits of 9..16 bits.
 //   G  > 1 : the shard is cut into V parts (virtual ranks g*V+q).  Counts of the full digit per
 //            part are known before the pass starts (first pass: counted; later: produced by the
 //            previous pass's exchange kernel), NCCL reduce-scatter/all-gather + digit-major /
@@ -16,8 +18,10 @@
 //            the owning GPU's other shard over NVLink (== :530-576) while the next part is being
 //            sorted.
 //
-// LSB_FLAG_TWO_STEP keeps round 1's shape for comparison: a 9..16-bit digit as two stable
-// 8-bit counting-sort steps over HBM (low bits, then high bits) -- the same permutation.
+// Which shape is the default is a measured choice: on one B200 both take
+// ~15.5 ms per 16-bit pass of 2^30 elements (the one-pass kernel is bound by its instruction
+// stream and barrier skew, the two steps by HBM), and next to an exchange kernel the one-pass
+// kernel's L2-resident scratch is evicted, so the two-step shape is the default.
 #include "../../include/lsbsort.h"
 #include "lsb_kernels.cuh"
 #include "lsb_onepass.cuh"
@@ -83,13 +87,19 @@ struct lsb_ctx {
   int num_sms = 0;
   int tile = TileCfg::TILE;           // elements per tile of partition_kernel
   int op_tile = TileCfg::TILE;        // elements per tile of onepass_kernel
-  // partition_kernel (digits of <= 8 bits, and LSB_FLAG_TWO_STEP)
+  // partition_kernel (two-step shape; digits of <= 8 bits)
   uint64_t* lookback = nullptr;
   size_t lookback_tiles = 0;
   uint32_t* tile_counters = nullptr;  // [TILE_COUNTERS], recycled
   int next_counter = 0;
   int gen = 0;
-  // digit counts of a whole sort (G == 1) / of one pass
+  int64_t* seg_start = nullptr;       // [1 + V][2]: {0, here}, then {0, m_q} per part
+  uint32_t* seg_tiles = nullptr;      // [1 + V][2]: {0, tiles}
+  // sub-digit counts of a whole sort, two-step shape (G == 1)
+  unsigned long long* hist = nullptr;        // [HIST_MAX_SUB][256]
+  int64_t* scan_out = nullptr;               // [HIST_MAX_SUB][257]
+  unsigned long long* host_hist = nullptr;   // pinned [HIST_MAX_SUB][256]
+  // digit counts of a whole sort (one-pass shape, G == 1) / of one pass
   unsigned long long* hist16 = nullptr;  // [<= 4 * 65536] counts of every pass's digit, compact
   int64_t* starts16 = nullptr;           // their exclusive scans (natural digit order)
   int* dig_meta = nullptr;               // [2][64] device: offset / bins per pass
@@ -206,7 +216,7 @@ PassPlan plan_pass(const lsb_ctx* c, int digit) {
   p.bits = std::min<int>(c->cfg.radix_bits, 64 - p.shift);
   // one-pass kernel: low BYTE, then the rest; two-step shape: balanced split (longer runs per bin)
   if (p.bits <= 8) p.lo_bits = 0;
-  else p.lo_bits = (c->cfg.flags & LSB_FLAG_TWO_STEP) ? p.bits / 2 : 8;
+  else p.lo_bits = (c->cfg.flags & LSB_FLAG_ONE_PASS) ? 8 : p.bits / 2;
   p.hi_bits = p.bits - p.lo_bits;
   return p;
 }
@@ -332,6 +342,55 @@ int launch_digit_hist(lsb_ctx* c, const Elt* src, int64_t m, const int* shift, c
   return LSB_OK;
 }
 
+// 256-bin histograms of up to HIST_MAX_SUB sub-digits in one read + their exclusive scans (two-step shape)
+int launch_subdigit_hist(lsb_ctx* c, const Elt* src, const SubPass* subs, int nsub) {
+  CU(c, cudaMemsetAsync(c->hist, 0, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, c->stream));
+  if (c->here > 0) {
+    HistArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = src;
+    a.m = c->here;
+    a.nsub = nsub;
+    for (int s = 0; s < nsub; s++) {
+      a.shift[s] = subs[s].shift;
+      a.mask[s] = (1u << subs[s].bits) - 1;
+    }
+    a.out = c->hist;
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * 4, div_ceil(c->here, HIST_THREADS));
+    bool bytes = true;  // sub-digits are exactly bytes 0..nsub-1 of the key (radix 8 and 16)
+    for (int s = 0; s < nsub; s++) bytes = bytes && subs[s].shift == 8 * s && subs[s].bits == 8;
+#define LSB_HIST(N, B) subdigit_hist_kernel<N, B><<<grid, HIST_THREADS, 0, c->stream>>>(a)
+    if (bytes && nsub == 8) LSB_HIST(8, true);
+    else switch (nsub) {
+      case 1: LSB_HIST(1, false); break;
+      case 2: LSB_HIST(2, false); break;
+      case 3: LSB_HIST(3, false); break;
+      case 4: LSB_HIST(4, false); break;
+      case 5: LSB_HIST(5, false); break;
+      case 6: LSB_HIST(6, false); break;
+      case 7: LSB_HIST(7, false); break;
+      case 8: LSB_HIST(8, false); break;
+      case 9: LSB_HIST(9, false); break;
+      case 10: LSB_HIST(10, false); break;
+      case 11: LSB_HIST(11, false); break;
+      case 12: LSB_HIST(12, false); break;
+      case 13: LSB_HIST(13, false); break;
+      case 14: LSB_HIST(14, false); break;
+      case 15: LSB_HIST(15, false); break;
+      default: LSB_HIST(16, false); break;
+    }
+#undef LSB_HIST
+    c->launches++;
+  }
+  CU(c, cudaGetLastError());
+  int rc = phase_mark(c, 0);
+  if (rc) return rc;
+  scan256_kernel<<<nsub, 256, 0, c->stream>>>(c->hist, c->scan_out);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return phase_mark(c, 1);
+}
+
 // exclusive scan of counts[G][nb] in digit-major, rank-minor order -> out[nb] = this rank's column
 int launch_scan(lsb_ctx* c, const unsigned long long* counts, int nb, int G, int my, int64_t* out, unsigned long long* sent) {
   GlobalScanArgs s;
@@ -350,7 +409,8 @@ int launch_scan(lsb_ctx* c, const unsigned long long* counts, int nb, int G, int
 
 // one stable counting-sort step on <= 8 bits over src[0, m): the whole pass for digits of <= 8
 // bits, half a pass in the two-step shape.  bases[bin] = first output index of the bin.
-int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits, const int64_t* bases, Elt* dst) {
+int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits, const int64_t* seg_start,
+                     const uint32_t* seg_tile_start, const int64_t* bases, Elt* dst) {
   if (c->gen > 126) {  // tags exhausted: wipe the look-back words and start over
     CU(c, cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
     c->gen = 0;
@@ -362,19 +422,23 @@ int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits,
   PartArgs a;
   memset(&a, 0, sizeof(a));
   a.src = src;
-  a.m = m;
   a.shift = shift;
   a.mask = (1u << bits) - 1;
+  a.seg_bits = 0;                    // one segment {0, m}: the whole input
+  a.seg_start = seg_start;
+  a.seg_tile_start = seg_tile_start;
   a.bases = bases;
   a.lookback = c->lookback;
   a.tile_counter = c->tile_counters + c->next_counter++;
   a.tag_agg = (uint64_t)(2 * c->gen + 1) << 56;
   a.tag_inc = (uint64_t)(2 * c->gen + 2) << 56;
   c->gen++;
-  a.dst = dst;
+  a.per = INT64_MAX / 16;
+  a.world = 1;
+  a.dst[0] = dst;
   c->part_elems += m;
   if (m > 0) {
-    partition_kernel<TileCfg><<<(unsigned)div_ceil(m, c->tile), TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+    partition_kernel<TileCfg, false><<<(unsigned)div_ceil(m, c->tile), TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
     c->launches++;
   }
   CU(c, cudaGetLastError());
@@ -544,7 +608,7 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     next_shift = q.shift;
     CU(c, cudaMemsetAsync(c->next_dense, 0, sizeof(unsigned) * (size_t)c->G * V * next_nb, c->stream));
   }
-  const bool two_step = p.lo_bits && (c->cfg.flags & LSB_FLAG_TWO_STEP);
+  const bool two_step = p.lo_bits && !(c->cfg.flags & LSB_FLAG_ONE_PASS);
   const bool timed = (c->cfg.flags & LSB_FLAG_PHASE_EVENTS) != 0;
   const int xbuf = c->cur ^ 1;
   int last_x = -1, prev_x = -1;
@@ -552,11 +616,13 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     const int64_t m = part_len(c, q);
     if (m <= 0) continue;
     Elt* part = c->buf[c->cur] + (int64_t)q * c->vpart;
+    const int64_t* segs = c->seg_start + 2 * (1 + q);
+    const uint32_t* tiles = c->seg_tiles + 2 * (1 + q);
     const Elt* sorted;
     if (two_step) {  // low step into the scratch, high step back in place
-      if ((rc = launch_partition(c, part, m, p.shift, p.lo_bits, c->bases_v + ((size_t)q * 2 + 0) * 257, c->scratch[0])))
+      if ((rc = launch_partition(c, part, m, p.shift, p.lo_bits, segs, tiles, c->bases_v + ((size_t)q * 2 + 0) * 257, c->scratch[0])))
         return rc;
-      if ((rc = launch_partition(c, c->scratch[0], m, p.shift + p.lo_bits, p.hi_bits,
+      if ((rc = launch_partition(c, c->scratch[0], m, p.shift + p.lo_bits, p.hi_bits, segs, tiles,
                                  c->bases_v + ((size_t)q * 2 + 1) * 257, part)))
         return rc;
       sorted = part;
@@ -565,7 +631,7 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
       Elt* out = c->scratch[q & 1];
       if (prev_x >= 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_x[prev_x], 0));  // scratch[q & 1] was read by that exchange
       if (p.lo_bits) rc = launch_onepass(c, part, out, m, p.shift, p.bits, c->localbase_v + (size_t)q * nb, 0, c->tune.op_ctas_mgpu);
-      else rc = launch_partition(c, part, m, p.shift, p.hi_bits, c->bases_v + ((size_t)q * 2 + 1) * 257, out);
+      else rc = launch_partition(c, part, m, p.shift, p.hi_bits, segs, tiles, c->bases_v + ((size_t)q * 2 + 1) * 257, out);
       if (rc) return rc;
       sorted = out;
       (*subpasses)++;
@@ -633,8 +699,40 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
 }
 
 // passes [d0, d1) on one GPU: one read counts the digits of every pass, then one launch per pass
-// (two in the LSB_FLAG_TWO_STEP shape) that reads the shard once and writes it once
+// (LSB_FLAG_ONE_PASS) or per 8-bit step (default) that reads the shard once and writes it once
 int passes_single(lsb_ctx* c, int d0, int d1, int* subpasses) {
+  if (!(c->cfg.flags & LSB_FLAG_ONE_PASS)) {
+    // two-step shape: one histogram read for all sub-digits, then one HBM -> HBM step per sub-digit
+    std::vector<SubPass> subs;
+    for (int d = d0; d < d1; d++) {
+      const PassPlan p = plan_pass(c, d);
+      if (p.lo_bits) subs.push_back({p.shift, p.lo_bits});
+      subs.push_back({p.shift + p.lo_bits, p.hi_bits});
+    }
+    int rc;
+    for (size_t s0 = 0; s0 < subs.size(); s0 += HIST_MAX_SUB) {
+      const int ns = (int)std::min<size_t>(HIST_MAX_SUB, subs.size() - s0);
+      if ((rc = launch_subdigit_hist(c, c->buf[c->cur], subs.data() + s0, ns))) return rc;
+      const bool may_skip = !(c->cfg.flags & LSB_FLAG_NO_SKIP) && c->here > 0;
+      if (may_skip) {  // a digit that is constant over the shard makes its stable step the identity
+        CU(c, cudaMemcpyAsync(c->host_hist, c->hist, sizeof(unsigned long long) * 256 * ns, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));  // once per sort (per 16 sub-digits), before the first step
+      }
+      for (int s = 0; s < ns; s++) {
+        const SubPass& sp = subs[s0 + s];
+        if (may_skip) {
+          bool constant = false;
+          for (int b = 0; b < 256; b++) constant = constant || c->host_hist[s * 256 + b] == (unsigned long long)c->here;
+          if (constant) { c->skipped++; continue; }
+        }
+        if ((rc = launch_partition(c, c->buf[c->cur], c->here, sp.shift, sp.bits, c->seg_start, c->seg_tiles, c->scan_out + (size_t)s * 257, c->buf[c->cur ^ 1])))
+          return rc;
+        c->cur ^= 1;
+        (*subpasses)++;
+      }
+    }
+    return LSB_OK;
+  }
   const int np = d1 - d0;
   int shift[64], bits[64], off[64], meta[128];
   int total = 0;
@@ -667,28 +765,8 @@ int passes_single(lsb_ctx* c, int d0, int d1, int* subpasses) {
     const PassPlan p = plan_pass(c, d0 + i);
     const int64_t* starts = c->starts16 + off[i];
     if (p.lo_bits == 0) {
-      rc = launch_partition(c, c->buf[c->cur], c->here, p.shift, p.bits, starts, c->buf[c->cur ^ 1]);
+      rc = launch_partition(c, c->buf[c->cur], c->here, p.shift, p.bits, c->seg_start, c->seg_tiles, starts, c->buf[c->cur ^ 1]);
       (*subpasses)++;
-    } else if (c->cfg.flags & LSB_FLAG_TWO_STEP) {
-      // bases of the two steps folded out of the digit's counts; one "part" = the whole shard
-      PartPrepArgs pp;
-      pp.counts = nullptr;
-      pp.counts64 = c->hist16 + off[i];
-      pp.nb = 1 << p.bits;
-      pp.lo_bits = p.lo_bits;
-      pp.hi_bits = p.hi_bits;
-      pp.localbase = c->localbase_v;
-      pp.bases = c->bases_v;
-      part_prep_kernel<<<1, 1024, 0, c->stream>>>(pp);
-      c->launches++;
-      if ((rc = launch_partition(c, c->buf[c->cur], c->here, p.shift, p.lo_bits, c->bases_v,
-                                 c->buf[c->cur ^ 1])))
-        return rc;
-      rc = launch_partition(c, c->buf[c->cur ^ 1], c->here, p.shift + p.lo_bits, p.hi_bits,
-                            c->bases_v + 257, c->buf[c->cur]);
-      (*subpasses) += 2;
-      if (rc) return rc;
-      continue;  // back in the same buffer
     } else {
       rc = launch_onepass(c, c->buf[c->cur], c->buf[c->cur ^ 1], c->here, p.shift, p.bits, starts, 0, 0);
       (*subpasses)++;
@@ -808,10 +886,13 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->buf[1], shard_bytes));
   c->peer[0][c->my] = c->buf[0];
   c->peer[1][c->my] = c->buf[1];
-  c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 2;
+  c->lookback_tiles = (size_t)div_ceil(c->per, c->tile) + 256 + 1;
   CUC(cudaMalloc(&c->lookback, c->lookback_tiles * 256 * sizeof(uint64_t)));
   CUC(cudaMemsetAsync(c->lookback, 0, c->lookback_tiles * 256 * sizeof(uint64_t), c->stream));
   CUC(cudaMalloc(&c->tile_counters, TILE_COUNTERS * sizeof(uint32_t)));
+  CUC(cudaMalloc(&c->hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB));
+  CUC(cudaMalloc(&c->scan_out, sizeof(int64_t) * 257 * HIST_MAX_SUB));
+  CUC(cudaHostAlloc(&c->host_hist, sizeof(unsigned long long) * 256 * HIST_MAX_SUB, cudaHostAllocDefault));
   CUC(cudaMalloc(&c->hist16, sizeof(unsigned long long) * 65536 * 4));
   CUC(cudaMalloc(&c->starts16, sizeof(int64_t) * 65536 * 4));
   CUC(cudaMalloc(&c->dig_meta, sizeof(int) * 128));
@@ -820,8 +901,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
   CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
   // one-pass kernel: supertile scratch, piece table, control block, frontier table
-  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
-  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
 #define LSB_OP_ATTR(CFG, B)                                                                                       \
   CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));     \
   CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -866,6 +947,22 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   c->two_level = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
   c->V = c->two_level ? c->tune.vparts : 1;
   c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
+  {
+    int64_t segs[2 * (1 + LSB_MAX_PARTS)];
+    uint32_t tls[2 * (1 + LSB_MAX_PARTS)];
+    for (int i = 0; i <= c->V; i++) {
+      const int64_t m = i == 0 ? c->here : part_len(c, i - 1);
+      segs[2 * i] = 0;
+      segs[2 * i + 1] = m;
+      tls[2 * i] = 0;
+      tls[2 * i + 1] = (uint32_t)div_ceil(m, c->tile);
+    }
+    CUC(cudaMalloc(&c->seg_start, sizeof(segs)));
+    CUC(cudaMalloc(&c->seg_tiles, sizeof(tls)));
+    CUC(cudaMemcpyAsync(c->seg_start, segs, sizeof(segs), cudaMemcpyHostToDevice, c->stream));
+    CUC(cudaMemcpyAsync(c->seg_tiles, tls, sizeof(tls), cudaMemcpyHostToDevice, c->stream));
+    CUC(cudaStreamSynchronize(c->stream));
+  }
   {  // tables of the two-step shape (G == 1: one part = the shard) and of the virtual ranks
     const int V = c->V;
     CUC(cudaMalloc(&c->localbase_v, sizeof(int64_t) * 65536 * V));
@@ -911,7 +1008,8 @@ void lsb_destroy(lsb_ctx* c) {
   if (c->comm) g_nccl.CommDestroy(c->comm);
   for (auto ev : c->phase_ev) cudaEventDestroy(ev);
   for (auto ev : c->xev) cudaEventDestroy(ev);
-  void* dev[] = {c->buf[0], c->buf[1], c->lookback, c->tile_counters, c->hist16, c->starts16, c->dig_meta, c->skip_flags,
+  if (c->host_hist) cudaFreeHost(c->host_hist);
+  void* dev[] = {c->seg_start, c->seg_tiles, c->hist, c->scan_out, c->buf[0], c->buf[1], c->lookback, c->tile_counters, c->hist16, c->starts16, c->dig_meta, c->skip_flags,
                  c->counts_all, c->mybase, c->op_ctl, c->op_X, c->op_oc, c->op_F, c->op_err, c->op_prof,
                  c->scratch[0], c->scratch[1], c->dense_local, c->dense_mine, c->next_dense, c->c_all, c->totals, c->digit_base,
                  c->mybase_v, c->localbase_v, c->bases_v, c->small, c->small_all};

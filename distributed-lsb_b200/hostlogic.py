@@ -36,13 +36,13 @@ def num_passes(radix_bits):
     return div_ceil(64, radix_bits)  # N_DIGITS (:22), ceil as chpl/arkouda-radix-sort.chpl:78-79
 
 
-def plan_pass(radix_bits, digit, two_step=False):
-    """(shift, bits, lo_bits, hi_bits) of reference pass `digit`: a digit wider than 8 bits is sorted by
-    its low byte (K1 of the one-pass kernel) and then by the rest (K2); LSB_FLAG_TWO_STEP splits it evenly
-    into two HBM steps instead (fewer bins per step = longer runs per bin)"""
+def plan_pass(radix_bits, digit, one_pass=False):
+    """(shift, bits, lo_bits, hi_bits) of reference pass `digit`: a digit wider than 8 bits is sorted as a
+    stable low-sub-digit step followed by a stable high-sub-digit step, split evenly (fewer bins per step =
+    longer runs per bin); LSB_FLAG_ONE_PASS sorts it by its low byte (K1) and then by the rest (K2)"""
     shift = radix_bits * digit
     bits = min(radix_bits, 64 - shift)
-    lo = 0 if bits <= 8 else (bits // 2 if two_step else 8)
+    lo = 0 if bits <= 8 else (8 if one_pass else bits // 2)
     return shift, bits, lo, bits - lo
 
 

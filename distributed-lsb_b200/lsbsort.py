@@ -26,7 +26,7 @@ LSB_MAX_SUBPASSES = 32
 LSB_COMM_ID_BYTES = 128
 FLAG_PHASE_EVENTS = 1
 FLAG_TWO_LEVEL = 2
-FLAG_TWO_STEP = 4
+FLAG_ONE_PASS = 4
 FLAG_NO_SKIP = 8
 
 

@@ -85,9 +85,9 @@ typedef struct lsb_config {
 #define LSB_FLAG_TWO_LEVEL 2u    /* run the multi-GPU pass shape (virtual ranks: per-part counts,
                                     digit-major / rank-minor scan, part sort + exchange kernel)
                                     even when world_size == 1                                  */
-#define LSB_FLAG_TWO_STEP 4u     /* sort a 9..16-bit digit as two stable 8-bit counting-sort steps
-                                    over HBM (round 1's shape, 64 B/element/pass) instead of the
-                                    one-pass kernel (32 B/element/pass); same permutation       */
+#define LSB_FLAG_ONE_PASS 4u     /* sort a 9..16-bit digit with the one-pass kernel: every element moves through
+                                    HBM once per reference pass (L2-resident supertiles) instead of twice (two
+                                    stable 8-bit counting-sort steps, the default); same permutation          */
 #define LSB_FLAG_NO_SKIP 8u      /* do not skip passes whose digit is constant over the shard
                                     (a stable pass on a constant digit is the identity; the
                                     reference always runs it; chpl passes nBits for the same
@@ -97,8 +97,8 @@ typedef struct lsb_config {
 typedef struct lsb_stats {
   double device_ms;       /* whole call: first kernel start -> last kernel end             */
   int32_t passes;         /* reference passes run (N_DIGITS, :22)                          */
-  int32_t subpasses;      /* scatter-kernel launches (1 per pass and part; 2 with TWO_STEP) */
-  int32_t skipped;        /* passes skipped because their digit was constant               */
+  int32_t subpasses;      /* scatter-kernel launches (2 per 16-bit pass and part; 1 with ONE_PASS) */
+  int32_t skipped;        /* steps (ONE_PASS: passes) skipped because their digit was constant */
   int32_t reserved0;
   int64_t elements;       /* elements of THIS shard that took part                         */
   double hist_ms;         /* count kernels (needs LSB_FLAG_PHASE_EVENTS, else 0)           */

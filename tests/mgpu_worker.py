@@ -36,8 +36,8 @@ def main():
     for ci, (n, R, bits, mask, k) in enumerate(cases):
         g = O.generate(n, R, key_mask=mask, and_draws=k)
         want = O.sort(g, n, R, bits)
-        # the part sort as one launch (default) or as two 8-bit steps (round 1's shape)
-        flags = [0, L.FLAG_TWO_STEP, L.FLAG_NO_SKIP][ci % 3]
+        # the part sort as two 8-bit steps (default) or as one launch of the one-pass kernel
+        flags = [0, L.FLAG_ONE_PASS, L.FLAG_NO_SKIP][ci % 3]
         s = make(n, R, rank, world, radix_bits=bits, key_mask=mask, and_draws=k, flags=flags)
         lo, hi = s.first_global, s.first_global + s.here
         s.generate()

@@ -34,7 +34,7 @@ def test_generate_matches_oracle(n, R, mask, k):
 
 @pytest.mark.parametrize("n,R", [(0, 1), (1, 1), (1, 4), (3, 4), (7, 3), (10, 8), (100, 4), (4095, 2), (4096, 1),
                                  (4097, 2), (65536, 4), (65537, 4), (1 << 20, 4), ((1 << 21) + 12345, 8)])
-@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL, L.FLAG_TWO_STEP])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL, L.FLAG_ONE_PASS, L.FLAG_TWO_LEVEL | L.FLAG_ONE_PASS])
 def test_sort_matches_oracle(n, R, flags):
     with lsb.DistributedSorter(n, ranks=R, flags=flags) as s:
         s.generate()
@@ -63,7 +63,7 @@ def test_config0_2pow24_r4_golden(golden_dir):
 
 
 @pytest.mark.parametrize("bits", [4, 8, 11, 13, 16])
-@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL, L.FLAG_ONE_PASS])
 def test_radix_widths(golden_dir, bits, flags):
     # config 5: digit width changes the pass count, never the answer
     final = _golden(golden_dir)["radix_n1048576_r4"]["final"]
@@ -78,7 +78,7 @@ def test_radix_widths(golden_dir, bits, flags):
 
 
 @pytest.mark.parametrize("bits", [8, 11, 16])
-@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL])
+@pytest.mark.parametrize("flags", [0, L.FLAG_TWO_LEVEL, L.FLAG_ONE_PASS, L.FLAG_TWO_LEVEL | L.FLAG_ONE_PASS])
 def test_each_pass_matches_reference_pass(golden_dir, bits, flags):
     """globalShuffle pass by pass: counts (:226-229), starts (:350,:407-413), array after (:546-575)"""
     gold = _golden(golden_dir)
@@ -101,7 +101,7 @@ def test_each_pass_matches_reference_pass(golden_dir, bits, flags):
 
 
 @pytest.mark.parametrize("mask,k", [(0xFFFFFF, 1), (ALL, 3), (0xFF, 1), (0, 1), (0xFFFF0000FFFF, 2)])
-@pytest.mark.parametrize("flags", [0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL])
+@pytest.mark.parametrize("flags", [0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL, L.FLAG_ONE_PASS, L.FLAG_ONE_PASS | L.FLAG_NO_SKIP])
 def test_skewed_keys_stable(mask, k, flags):
     # config 4: single-bin digits, massive ties; stability decides the answer
     n, R = 700001, 4
@@ -118,21 +118,22 @@ def test_skewed_keys_stable(mask, k, flags):
 
 
 def test_constant_digits_are_skipped_not_missorted():
-    # 24-bit keys: digits 2 and 3 are constant -> 2 of the 4 passes are skipped, same bytes out
+    # 24-bit keys: sub-digits 3..7 (digits 2 and 3) are constant -> their steps are skipped, same bytes out
     n, R = 300000, 2
     g = O.generate(n, R, key_mask=0xFFFFFF)
     want = O.sort(g, n, R)
-    for flags, skipped in ((0, 2), (L.FLAG_NO_SKIP, 0)):
+    for flags, skipped, total in ((0, 5, 8), (L.FLAG_NO_SKIP, 0, 8), (L.FLAG_ONE_PASS, 2, 4), (L.FLAG_ONE_PASS | L.FLAG_NO_SKIP, 0, 4)):
         with lsb.DistributedSorter(n, ranks=R, key_mask=0xFFFFFF, flags=flags) as s:
             s.generate()
             st = s.my_sort()
-            assert st.skipped == skipped and st.subpasses == 4 - skipped and st.passes == 4
+            assert st.skipped == skipped and st.subpasses == total - skipped and st.passes == 4
             assert (s.download() == want).all()
-    with lsb.DistributedSorter(1000, key_mask=0) as s:  # every digit constant: nothing to do at all
-        s.generate()
-        st = s.my_sort()
-        assert st.subpasses == 0 and st.skipped == 4
-        assert (s.download() == O.generate(1000, 1, key_mask=0)[:1000]).all()
+    for flags, total in ((0, 8), (L.FLAG_ONE_PASS, 4)):
+        with lsb.DistributedSorter(1000, key_mask=0, flags=flags) as s:  # every digit constant: nothing to do at all
+            s.generate()
+            st = s.my_sort()
+            assert st.subpasses == 0 and st.skipped == total
+            assert (s.download() == O.generate(1000, 1, key_mask=0)[:1000]).all()
 
 
 @pytest.mark.parametrize("t1,nx,lead,cfg", [(1, 2, 1, 1), (3, 3, 1, 0), (7, 4, 2, 1), (5, 6, 3, 1)])
@@ -148,7 +149,7 @@ def test_onepass_many_small_supertiles(t1, nx, lead, cfg, mask, k, bits):
     lsb.tune("op_lead", lead)
     lsb.tune("op_cfg", cfg)
     try:
-        with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, key_mask=mask, and_draws=k, flags=L.FLAG_NO_SKIP) as s:
+        with lsb.DistributedSorter(n, ranks=R, radix_bits=bits, key_mask=mask, and_draws=k, flags=L.FLAG_NO_SKIP | L.FLAG_ONE_PASS) as s:
             s.generate()
             s.my_sort()
             assert (s.download() == want).all()
@@ -167,7 +168,7 @@ def test_grouped_upper_bits_large_ragged_n():
     a["key"] = (hi << np.uint64(32)) | rng.integers(0, 1 << 32, n, dtype=np.uint64)
     a["val"] = np.arange(n, dtype=np.uint64)
     want = O.stable_sort(a, n)
-    for flags in (0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL):
+    for flags in (0, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL, L.FLAG_ONE_PASS):
         with lsb.DistributedSorter(n, flags=flags) as s:
             s.upload(a)
             for p in range(4):
@@ -226,10 +227,10 @@ def test_repeated_sorts_reuse_context():
         assert (s.download() == want).all()
 
 
-@pytest.mark.parametrize("n", [1 << 26, 1 << 28])
-def test_large_properties(n):
+@pytest.mark.parametrize("n,flags", [(1 << 26, 0), (1 << 28, 0), (1 << 26, L.FLAG_ONE_PASS), (1 << 28, L.FLAG_ONE_PASS)])
+def test_large_properties(n, flags):
     # sizes with no CPU oracle: strictly increasing (key,val) + same multiset == stable sort
-    with lsb.DistributedSorter(n, ranks=1) as s:
+    with lsb.DistributedSorter(n, ranks=1, flags=flags) as s:
         s.generate()
         before = s.checksum()
         assert before[3] == (n * (n - 1) // 2) % (1 << 64)
@@ -239,7 +240,7 @@ def test_large_properties(n):
         # idempotence: sorting sorted data changes nothing
         s.my_sort()
         assert list(s.verify().checksum) == before
-    assert st.subpasses == 4
+    assert st.subpasses == (4 if flags & L.FLAG_ONE_PASS else 8)
 
 
 def test_errors_are_reported_not_swallowed():
@@ -309,7 +310,7 @@ def test_randomised_parity_sweep():
         bits = int(rng.choice([1, 3, 5, 7, 8, 9, 10, 11, 12, 14, 15, 16])) if case % 3 == 0 else 16
         mask = masks[int(rng.integers(0, len(masks)))]
         k = int(rng.integers(1, 4))
-        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_TWO_STEP, L.FLAG_TWO_STEP][case % 5]
+        flags = [0, L.FLAG_TWO_LEVEL, L.FLAG_NO_SKIP, L.FLAG_TWO_LEVEL | L.FLAG_ONE_PASS, L.FLAG_ONE_PASS][case % 5]
         if bits < 4 and n > 20000:
             n = 20000  # 64 passes of a 1-bit digit: keep the oracle quick
         g = O.generate(n, R, key_mask=mask, and_draws=k)

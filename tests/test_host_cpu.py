@@ -29,9 +29,9 @@ def test_distribution_matches_oracle(n, R):
 def test_subpass_plan():
     assert H.num_passes(16) == 4 and H.num_passes(11) == 6 and H.num_passes(8) == 8
     assert H.subpasses(16) == [(0, 8), (8, 8), (16, 8), (24, 8), (32, 8), (40, 8), (48, 8), (56, 8)]
-    assert H.plan_pass(11, 5) == (55, 9, 8, 1)  # the last 11-bit digit is 9 bits wide: low byte + 1 bit
-    assert H.plan_pass(11, 5, two_step=True) == (55, 9, 4, 5)
-    assert H.plan_pass(11, 0) == (0, 11, 8, 3) and H.plan_pass(16, 1) == (16, 16, 8, 8)
+    assert H.plan_pass(11, 5) == (55, 9, 4, 5)  # the last 11-bit digit is 9 bits wide
+    assert H.plan_pass(11, 5, one_pass=True) == (55, 9, 8, 1)  # one-pass kernel: low byte + 1 bit
+    assert H.plan_pass(11, 0) == (0, 11, 5, 6) and H.plan_pass(16, 1) == (16, 16, 8, 8)
     assert H.subpasses(8) == [(8 * i, 8) for i in range(8)]
     for bits in range(1, 17):  # sub-digits tile the key exactly once
         covered = sorted(b for s, w in H.subpasses(bits) for b in range(s, s + w))

@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=28, help="log2 elements per GPU")
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--radix", type=int, default=16)
-ap.add_argument("--two-step", action="store_true")
+ap.add_argument("--one-pass", action="store_true")
 ap.add_argument("--mask", type=lambda x: int(x, 0), default=0xFFFFFFFFFFFFFFFF)
 ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune, repeatable")
 a = ap.parse_args()
@@ -27,7 +27,7 @@ torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 n = world << a.log2n
 s = lsb.DistributedSorter(n, ranks=world, world_size=world, world_rank=rank, device=lr, radix_bits=a.radix,
-                          key_mask=a.mask, flags=L.FLAG_PHASE_EVENTS | L.FLAG_NO_SKIP | (L.FLAG_TWO_STEP if a.two_step else 0))
+                          key_mask=a.mask, flags=L.FLAG_PHASE_EVENTS | L.FLAG_NO_SKIP | (L.FLAG_ONE_PASS if a.one_pass else 0))
 ids = [lsb.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 s.comm_init(ids[0])
@@ -41,7 +41,7 @@ for i in range(a.iters):
         m = s.here
         tail = (f"exchange kernels {st.exchange_ms:.2f} ms busy = "
                 f"{m * 16 * (world - 1) / world * st.passes / max(st.exchange_ms, 1e-9) / 1e6:.0f} GB/s out per GPU while running")
-        print(f"[{' '.join(a.tune) or 'default'}{' two-step' if a.two_step else ''}] iter {i}: sort {st.device_ms:.2f} ms = {n / st.device_ms / 1e3:.0f} M elem/s; count {st.hist_ms:.2f} ms, "
+        print(f"[{' '.join(a.tune) or 'default'}{' one-pass' if a.one_pass else ''}] iter {i}: sort {st.device_ms:.2f} ms = {n / st.device_ms / 1e3:.0f} M elem/s; count {st.hist_ms:.2f} ms, "
               f"scan+coll {st.scan_ms:.2f} ms, partitions {sub} ms; sent {list(st.sent[:world])}; {tail}", flush=True)
 s.close()
 dist.destroy_process_group()

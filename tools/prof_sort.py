@@ -13,7 +13,7 @@ ap.add_argument("--log2n", type=int, default=26)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--radix", type=int, default=16)
 ap.add_argument("--two-level", action="store_true")
-ap.add_argument("--two-step", action="store_true")
+ap.add_argument("--one-pass", action="store_true", help="LSB_FLAG_ONE_PASS: the one-pass kernel instead of two 8-bit steps")
 ap.add_argument("--no-skip", action="store_true")
 ap.add_argument("--mask", type=lambda x: int(x, 0), default=0xFFFFFFFFFFFFFFFF)
 ap.add_argument("--and-draws", type=int, default=1)
@@ -22,7 +22,7 @@ a = ap.parse_args()
 for kv in a.tune:
     k, v = kv.split("=")
     lsb.tune(k, int(v))
-flags = (L.FLAG_PHASE_EVENTS | (L.FLAG_TWO_LEVEL if a.two_level else 0) | (L.FLAG_TWO_STEP if a.two_step else 0)
+flags = (L.FLAG_PHASE_EVENTS | (L.FLAG_TWO_LEVEL if a.two_level else 0) | (L.FLAG_ONE_PASS if a.one_pass else 0)
          | (L.FLAG_NO_SKIP if a.no_skip else 0))
 with lsb.DistributedSorter(1 << a.log2n, ranks=1, radix_bits=a.radix, key_mask=a.mask, and_draws=a.and_draws, flags=flags) as s:
     for i in range(a.iters):

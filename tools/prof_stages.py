@@ -26,7 +26,7 @@ for kv in a.tune:
 n = 1 << a.log2n
 lib = lsb.load_library()
 lib.lsb_debug_prof.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-with lsb.DistributedSorter(n, ranks=1, flags=L.FLAG_NO_SKIP) as s:
+with lsb.DistributedSorter(n, ranks=1, flags=L.FLAG_NO_SKIP | L.FLAG_ONE_PASS) as s:
     s.generate()
     s.my_sort()
     out = (ctypes.c_uint64 * 24)()

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """One-GPU sweep of the one-pass kernel's tunables (lsb_tune): prints sort time per configuration.
-    python tools/sweep_onepass.py --log2n 30 --set op_t1=238,op_nx=3,op_hints=7 --set op_t1=128 ..."""
+    python tools/sweep_onepass.py --log2n 30 --set op_lead=2,op_nx=4 --set op_t1=128 --set two_step ...
+Every configuration runs with LSB_FLAG_ONE_PASS except the one named `two_step` (the default shape)."""
 import argparse
 import os
 import sys
@@ -16,15 +17,15 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--radix", type=int, default=16)
 ap.add_argument("--mask", type=lambda x: int(x, 0), default=0xFFFFFFFFFFFFFFFF)
 ap.add_argument("--and-draws", type=int, default=1)
-ap.add_argument("--set", action="append", default=[], help="comma-separated key=value list; 'two_step' = round-1 shape")
+ap.add_argument("--set", action="append", default=[], help="comma-separated key=value list; 'two_step' = the default two-step shape")
 a = ap.parse_args()
 n = 1 << a.log2n
 for cfg in a.set or [""]:
-    flags = L.FLAG_PHASE_EVENTS | L.FLAG_NO_SKIP
+    flags = L.FLAG_PHASE_EVENTS | L.FLAG_NO_SKIP | L.FLAG_ONE_PASS
     kv = dict(DEFAULTS)
     for item in filter(None, cfg.split(",")):
         if item == "two_step":
-            flags |= L.FLAG_TWO_STEP
+            flags &= ~L.FLAG_ONE_PASS
         elif item == "two_level":
             flags |= L.FLAG_TWO_LEVEL
         else:
