@@ -183,7 +183,7 @@ def workload_name(gpus, args):
 # --------------------------------------------------------------------------------------
 # this repo's arm
 # --------------------------------------------------------------------------------------
-def main_cuda(args, rank, world, local_rank):
+def main_cuda(args, rank, world, local_rank, own_process_group=True, tag=None):
     import torch
     import torch.distributed as dist
     import distributed_lsb_b200 as lsb
@@ -192,7 +192,7 @@ def main_cuda(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    if world > 1:
+    if world > 1 and own_process_group:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -416,10 +416,35 @@ def main_cuda(args, rank, world, local_rank):
             line["alt_path"] = alt_path
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
-    if world > 1:
+        if tag:
+            line = dict({"suite": tag}, **line)
+        print(json.dumps(line), flush=True)
+    if world > 1 and own_process_group:
         dist.destroy_process_group()
     return 0
+
+
+def main_suite(args, rank, world, local_rank, parser):
+    """several configurations in ONE set of processes (a multi-GPU box is charged per GPU-minute: import, NCCL and
+    rendezvous are paid once).  --suite 'weak:;strong:--strong;mask24:--key-mask 0xFFFFFF --no-e2e;...'"""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rc = 0
+    for item in filter(None, (x.strip() for x in args.suite.split(";"))):
+        name, _, extra = item.partition(":")
+        sub = parser.parse_args(["--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)] + extra.split())
+        try:
+            main_cuda(sub, rank, world, local_rank, own_process_group=False, tag=name)
+        except SystemExit as e:  # keep going: the other configurations are still worth their GPU time
+            if rank == 0:
+                print(json.dumps({"suite": name, "error": str(e)}), flush=True)
+            rc = 1
+    if world > 1:
+        dist.destroy_process_group()
+    return rc
 
 
 def main():
@@ -442,6 +467,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune (experiments)")
     ap.add_argument("--one-pass", action="store_true", help="measure LSB_FLAG_ONE_PASS (the one-pass kernel) as the main path")
     ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other pass shape (N = 1)")
+    ap.add_argument("--suite", default="", help="'name:flags;name:flags;...': several configurations in one launch, one JSON line each")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -457,6 +483,8 @@ def main():
     if args.impl == "reference":
         return main_reference(args, rank)
     try:
+        if args.suite:
+            return main_suite(args, rank, world, local_rank, ap)
         return main_cuda(args, rank, world, local_rank)
     except BaseException:  # a rank that dies quietly would leave its peers waiting in a collective
         import traceback

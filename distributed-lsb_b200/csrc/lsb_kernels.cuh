@@ -751,8 +751,6 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
 // TLB set conflicts on cross-process peer mappings) when the 22-element runs of the scatter
 // kernel are stored remotely (tools/p2p_bench.cu, tools/p2p_ipc_bench.cu).
 // ------------------------------------------------------------------------------------
-constexpr int EX_U = 4;  // 16-byte elements in flight per thread
-
 // ------------------------------------------------------------------------------------
 // Pipelined multi-GPU pass ("virtual ranks"): every shard is cut into V contiguous parts and
 // part q of GPU g acts as rank g*V+q of the reference's algorithm (its order is the global
@@ -892,7 +890,8 @@ struct ExchVrArgs {
 
 // EX_THREADS = 512 when the exchange has the SMs to itself or shares them with partition_kernel CTAs that
 // come and go; 256 (12.8 K registers) fits beside three resident CTAs of the persistent one-pass kernel.
-template <int EX_THREADS>
+// EX_U = 16-byte elements in flight per thread.
+template <int EX_THREADS, int EX_U>
 __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArgs a) {
   __shared__ Elt* s_dst[8];
   __shared__ long long s_lim[8];

@@ -66,7 +66,8 @@ struct Tuning {
   int op_ctas_mgpu = 3;  // one-pass CTAs per SM while an exchange kernel shares the GPU (G > 1)
   int vparts = 8;        // parts per shard of the multi-GPU pass
   int ex_ctas = 1;       // exchange CTAs per SM
-  int ex_threads = 256;  // threads per exchange CTA (256 or 512)
+  int ex_threads = 0;    // threads per exchange CTA (256 or 512; 0 = by pass shape)
+  int ex_u = 4;          // 16-byte elements in flight per exchange thread (4 or 8)
   int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
 };
 Tuning g_tune;
@@ -662,10 +663,13 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     x.next_nb = next_nb;
     x.part = c->vpart;
     x.next_dense = c->next_dense;
-    const int ex_threads = c->tune.ex_threads == 256 ? 256 : 512;
-    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->tune.ex_ctas, div_ceil(m, (int64_t)ex_threads * EX_U));
-    if (ex_threads == 256) exchange_vr_kernel<256><<<grid, 256, 0, c->xstream>>>(x);
-    else exchange_vr_kernel<512><<<grid, 512, 0, c->xstream>>>(x);
+    // 512 threads next to partition_kernel CTAs that come and go; 256 fit beside three resident one-pass CTAs
+    const int ex_threads = c->tune.ex_threads ? c->tune.ex_threads : ((c->cfg.flags & LSB_FLAG_ONE_PASS) ? 256 : 512);
+    const int ex_u = c->tune.ex_u == 8 ? 8 : 4;
+    const int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->tune.ex_ctas, div_ceil(m, (int64_t)ex_threads * ex_u));
+    if (ex_threads == 256) exchange_vr_kernel<256, 4><<<grid, 256, 0, c->xstream>>>(x);
+    else if (ex_u == 8) exchange_vr_kernel<512, 8><<<grid, 512, 0, c->xstream>>>(x);
+    else exchange_vr_kernel<512, 4><<<grid, 512, 0, c->xstream>>>(x);
     c->launches++;
     CU(c, cudaGetLastError());
     if (timed) {
@@ -819,7 +823,8 @@ int lsb_tune(const char* key, int value) {
   else if (k == "op_ctas_mgpu" && value >= 0 && value <= 4) g_tune.op_ctas_mgpu = value;
   else if (k == "vparts" && value >= 1 && value <= LSB_MAX_PARTS) g_tune.vparts = value;
   else if (k == "ex_ctas" && value >= 1 && value <= 8) g_tune.ex_ctas = value;
-  else if (k == "ex_threads" && (value == 256 || value == 512)) g_tune.ex_threads = value;
+  else if (k == "ex_threads" && (value == 0 || value == 256 || value == 512)) g_tune.ex_threads = value;
+  else if (k == "ex_u" && (value == 4 || value == 8)) g_tune.ex_u = value;
   else if (k == "timeout_ms" && value >= 1) g_tune.timeout_ms = value;
   else return fail(nullptr, LSB_ERR_ARG, "lsb_tune: unknown key or value out of range: " + k);
   return LSB_OK;

@@ -31,6 +31,7 @@ struct Options {
   int64_t n = 100 * 1000 * 1000;  // :593
   bool print = false, verify = false, verify_set = false;
   int gpus = 1, ranks = 0, radix = 16, and_draws = 1;
+  bool one_pass = false;
   uint64_t key_mask = ~0ULL, seed_base = 0;
 };
 
@@ -103,7 +104,7 @@ int worker(const Options& o, int g, int up, int down) {
   cfg.and_draws = o.and_draws;
   cfg.seed_base = o.seed_base;
   cfg.key_mask = o.key_mask;
-  cfg.flags = LSB_FLAG_PHASE_EVENTS;
+  cfg.flags = LSB_FLAG_PHASE_EVENTS | (o.one_pass ? LSB_FLAG_ONE_PASS : 0u);
   lsb_ctx* c = nullptr;
   int rc = lsb_create(&c, &cfg);
   if (rc) die("lsb_create", nullptr, rc);
@@ -193,10 +194,11 @@ int main(int argc, char** argv) {
     else if (a == "--radix") o.radix = std::atoi(next());
     else if (a == "--key-mask") o.key_mask = std::strtoull(next(), nullptr, 0);
     else if (a == "--and-draws") o.and_draws = std::atoi(next());
+    else if (a == "--one-pass") o.one_pass = true;
     else if (a == "--seed-base") o.seed_base = std::strtoull(next(), nullptr, 0);
     else if (a == "--help" || a == "-h") {
       std::printf("usage: lsbsort [--n N] [--gpus G] [--ranks R] [--radix BITS] [--verify|--no-verify] [--print]\n"
-                  "               [--key-mask M] [--and-draws K] [--seed-base S]\n");
+                  "               [--key-mask M] [--and-draws K] [--seed-base S] [--one-pass]\n");
       return 0;
     }
   }

@@ -216,6 +216,24 @@ def test_verifier_rejects_unsorted_and_unstable():
             s.verify()
 
 
+def test_many_partition_launches_recycle_tile_counters():
+    # radix 2 with the virtual-rank shape: 32 passes x 8 parts = 256 launches per sort, 3 sorts on one context
+    # (the per-launch tile counters are recycled in stream order once all 1024 have been used)
+    n = 40000
+    want = O.sort(O.generate(n, 2), n, 2, 2)
+    with lsb.DistributedSorter(n, ranks=2, radix_bits=2, flags=L.FLAG_TWO_LEVEL) as s:
+        for _ in range(3):
+            s.generate()
+            s.my_sort()
+            assert (s.download() == want).all()
+    want1 = O.sort(O.generate(3000, 1), 3000, 1, 1)
+    with lsb.DistributedSorter(3000, ranks=1, radix_bits=1, flags=L.FLAG_TWO_LEVEL) as s:  # 64 passes x 8 parts
+        for _ in range(3):
+            s.generate()
+            s.my_sort()
+        assert (s.download() == want1).all()
+
+
 def test_repeated_sorts_reuse_context():
     # look-back words are tagged by generation instead of being cleared: exercise the wrap
     n = 50000

@@ -39,6 +39,24 @@ __global__ void scatter_frontier(const Elt* __restrict__ src, Elt* dst, Elt* dst
   }
 }
 
+// the same pattern with `nb` frontiers (nb = 65536: a single-step 16-bit scatter): tiles of nb * run elements in
+// input order, each appends `run` elements to every one of nb frontiers that are n / nb apart.  run = 1 is the
+// "one-element appends into 65 536 tile-ordered frontiers" case: nothing coalesces inside a warp, every 128-byte
+// output line is completed by 8 consecutive tiles, and 65 536 x 128 B = 8 MiB of lines are open in L2 at a time.
+__global__ void scatter_frontier_nb(const Elt* __restrict__ src, Elt* dst, int64_t n, int nb, int run) {
+  const int64_t T = (int64_t)nb * run;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t region = n / nb;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t tile = i / T;
+    const int64_t p = i - tile * T;
+    const int64_t bin = p / run;
+    const int off = (int)(p - bin * run);
+    Elt e = src[i];
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + bin * region + tile * run + off), "l"(e.k), "l"(e.v) : "memory");
+  }
+}
+
 // same, with L2 eviction-priority hints: mode bit0 = loads evict_first, bit1 = stores evict_last,
 // bit2 = stores evict_first
 __global__ void scatter_frontier_hint(const Elt* __restrict__ src, Elt* dst, int64_t n, int T, int mode) {
@@ -114,6 +132,20 @@ int main(int argc, char** argv) {
       printf("local frontier pattern T=%d (run %d el = %d B): %.2f ms, %.0f GB/s read+write\n", T, T / 256, T / 16, ms,
              n * 32.0 / ms / 1e6);
     }
+    for (int nb : {256, 4096, 65536})
+      for (int run : {1, 2, 4, 8, 10, 16, 22}) {
+        if ((int64_t)nb * run > n) continue;
+        float ms = 0;
+        for (int rep = 0; rep < 3; rep++) {
+          CK(cudaEventRecord(a));
+          scatter_frontier_nb<<<148 * 8, 512>>>(src, dst, n, nb, run);
+          CK(cudaEventRecord(b));
+          CK(cudaEventSynchronize(b));
+          CK(cudaEventElapsedTime(&ms, a, b));
+        }
+        printf("%d tile-ordered frontiers, %d-element (%d B) appends: %.2f ms, %.0f GB/s read+write\n", nb, run, run * 16, ms,
+               n * 32.0 / ms / 1e6);
+      }
     for (int T : {2816, 5632, 8448, 11264}) {
       float ms = 0;
       for (int rep = 0; rep < 3; rep++) {
