@@ -903,6 +903,7 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArg
     }
   }
   __syncthreads();
+  unsigned pend_slot = 0xffffffffu, pend_cnt = 0;
   const int64_t chunk = (int64_t)EX_THREADS * EX_U;
   const int64_t span = ((a.m + a.world - 1) / a.world + chunk - 1) / chunk * chunk;
   const int64_t chunks_per_span = span / chunk;
@@ -930,11 +931,47 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArg
           int v = (int)(j / a.part);
           v = v < a.V ? v : a.V - 1;
           const unsigned dn = (unsigned)(e[u].key >> a.next_shift) & a.next_mask;
-          atomicAdd(a.next_dense + ((size_t)(r * a.V + v) * a.next_nb + dn), 1u);
+          const unsigned slot = (unsigned)(r * a.V + v) * (unsigned)a.next_nb + dn;
+          // skew: when the whole warp counts into one slot, one lane adds the population count; a thread also
+          // holds back a run of equal slots and adds it once (constant digits: one atomic per thread per launch)
+          const unsigned act = __activemask();
+          const int leader = __ffs(act) - 1;
+          const bool same = __all_sync(act, slot == __shfl_sync(act, slot, leader));
+          const unsigned cnt = same ? (((int)(threadIdx.x & 31) == leader) ? (unsigned)__popc(act) : 0u) : 1u;
+          if (cnt) {
+            if (slot == pend_slot) pend_cnt += cnt;
+            else {
+              if (pend_cnt) atomicAdd(a.next_dense + pend_slot, pend_cnt);
+              pend_slot = slot;
+              pend_cnt = cnt;
+            }
+          }
         }
       }
     }
   }
+  if (pend_cnt) atomicAdd(a.next_dense + pend_slot, pend_cnt);
+}
+
+// How many distinct values does digit (shift, mask) take over the first `m` (<= 65 536) elements?  The exchange
+// kernel's fused next-digit count uses one L2 atomic per element, which is only cheap when the digit has thousands
+// of live bins; the host reads this estimate (minimum over the GPUs) to decide per pass.
+__global__ void __launch_bounds__(1024) live_bins_kernel(const Elt* src, int m, int shift, uint32_t mask, unsigned* out) {
+  __shared__ unsigned bits[2048];  // 65 536-bit bitmap
+  __shared__ unsigned total;
+  for (int i = threadIdx.x; i < 2048; i += 1024) bits[i] = 0;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += 1024) {
+    const unsigned d = (unsigned)(ld_stream_key(src + i) >> shift) & mask;
+    atomicOr(&bits[d >> 5], 1u << (d & 31));
+  }
+  __syncthreads();
+  unsigned c = 0;
+  for (int i = threadIdx.x; i < 2048; i += 1024) c += __popc(bits[i]);
+  atomicAdd(&total, c);
+  __syncthreads();
+  if (threadIdx.x == 0) *out = total;
 }
 
 // ------------------------------------------------------------------------------------

@@ -583,6 +583,42 @@ int part_offsets(lsb_ctx* c, int digit) {
   return LSB_OK;
 }
 
+// c_all (counts of every virtual rank) -> does one digit value hold all n elements?
+int digit_is_constant(lsb_ctx* c, int digit, bool* constant) {
+  const PassPlan p = plan_pass(c, digit);
+  const int nb = 1 << p.bits;
+  VrScanArgs v;
+  memset(&v, 0, sizeof(v));
+  v.counts = c->c_all;
+  v.nb = nb;
+  v.GV = c->G * c->V;
+  v.totals = c->totals;
+  vr_totals_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(v);
+  const int meta[2] = {0, nb};
+  CU(c, cudaMemcpyAsync(c->dig_meta, meta, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->dig_meta + 64, meta + 1, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  constant_digit_kernel<<<1, 256, 0, c->stream>>>(c->totals, c->dig_meta, c->dig_meta + 64, (unsigned long long)c->n, c->skip_flags);
+  c->launches += 2;
+  CU(c, cudaMemcpyAsync(c->host_skip, c->skip_flags, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *constant = c->host_skip[0] != 0;
+  return LSB_OK;
+}
+
+// distinct values of digit q among the first 65 536 elements of the shard, minimum over the GPUs
+int sample_live_bins(lsb_ctx* c, const PassPlan& q, int* live) {
+  unsigned* d = reinterpret_cast<unsigned*>(c->small + 36);
+  const int m = (int)std::min<int64_t>(c->here, 65536);
+  live_bins_kernel<<<1, 1024, 0, c->stream>>>(c->buf[c->cur], m, q.shift, (uint32_t)((1u << q.bits) - 1), d);
+  c->launches++;
+  CU(c, cudaGetLastError());
+  if (c->G > 1) NC(c, g_nccl.AllReduce(d, d, 1, ncclUint32, ncclMin, c->comm, c->stream));
+  CU(c, cudaMemcpyAsync(c->host_skip + 8, d, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  *live = c->host_skip[8];
+  return LSB_OK;
+}
+
 // one reference pass, pipelined over V parts of the shard (virtual ranks g*V+q):
 //   counts of the full digit of every part are known up front (first pass: counted here; later
 //   passes: produced by the previous pass's exchange kernel), so
@@ -598,11 +634,33 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     if ((rc = phase_mark(c, 0))) return rc;
   }
   c->dense_ready_digit = -1;
+  if (!(c->cfg.flags & LSB_FLAG_NO_SKIP) && c->n > 0) {
+    // a digit that is constant over the WHOLE array makes the pass the identity (every GPU sees the same
+    // counts of all virtual ranks, so every GPU takes the same decision)
+    bool constant = false;
+    if ((rc = digit_is_constant(c, digit, &constant))) return rc;
+    if (constant) {  // identity pass: every element stays where it is (sendCounts: everything to myself)
+      c->skipped++;
+      unsigned long long* sent = c->host_small + 140;
+      for (int g = 0; g < 8; g++) sent[g] = (g == c->my) ? (unsigned long long)c->here : 0ULL;
+      CU(c, cudaMemcpyAsync(c->small, sent, 8 * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+      return phase_mark(c, 1);
+    }
+  }
   if ((rc = part_offsets(c, digit))) return rc;
   if ((rc = phase_mark(c, 1))) return rc;
 
+  // The exchange kernel counts the NEXT pass's digit per (destination GPU, destination part) with one L2 atomic per
+  // element -- cheap when the digit has thousands of bins (lanes of a warp rarely collide), ruinous for narrow digits
+  // (radix 8: 256 bins, every warp instruction replays ~32 times: 131 ms per pass measured).  Narrow digits are
+  // counted by the shared-memory count kernel at the start of their own pass instead (one extra 16 B/element read).
   int next_nb = 0, next_shift = 0;
-  const bool has_next = fuse_next && digit + 1 < c->npasses;
+  bool has_next = fuse_next && digit + 1 < c->npasses && plan_pass(c, digit + 1).bits >= 12;
+  if (has_next) {  // ... and wide digits that are narrow in THIS data (skewed keys), judged from a sample
+    int live = 0;
+    if ((rc = sample_live_bins(c, plan_pass(c, digit + 1), &live))) return rc;
+    has_next = live >= 2048;
+  }
   if (has_next) {
     const PassPlan q = plan_pass(c, digit + 1);
     next_nb = 1 << q.bits;

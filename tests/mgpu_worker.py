@@ -49,21 +49,22 @@ def main():
         assert v.elements == n and list(v.checksum) == O.checksum(g[:n]), ("verify", n)
         assert sum(st.sent[:world]) == s.here
         s.close()
-    # pass by pass against the reference's per-pass tables, ranks == GPUs
-    n, bits = 1 << 20, 16
-    a = O.generate(n, world)[:n]
-    s = make(n, world, rank, world, radix_bits=bits)
-    s.generate()
-    lo, hi = s.first_global, s.first_global + s.here
-    for p in range(s.num_passes()):
-        want, counts, starts, sc = O.one_pass(a, n, world, bits, p)
-        assert (s.histogram(p) == counts[rank]).all(), ("counts", p)
-        assert (s.starts(p) == starts[:, rank]).all(), ("starts", p)
-        st = s.global_shuffle(p)
-        assert list(st.sent[:world]) == sc[rank].tolist(), ("sendcounts", p, list(st.sent[:world]), sc[rank].tolist())
-        a = want
-        assert (s.download() == a[lo:hi]).all(), ("array after pass", p)
-    s.close()
+    # pass by pass against the reference's per-pass tables, ranks == GPUs: the default (pipelined, virtual ranks)
+    # pass at a size where a part is a single tile and at one where it is dozens of tiles, then the one-pass part sort
+    for n, bits, flags in ((1 << 20, 16, 0), (1 << 24, 16, 0), (1 << 22, 16, L.FLAG_ONE_PASS)):
+        a = O.generate(n, world)[:n]
+        s = make(n, world, rank, world, radix_bits=bits, flags=flags)
+        s.generate()
+        lo, hi = s.first_global, s.first_global + s.here
+        for p in range(s.num_passes()):
+            want, counts, starts, sc = O.one_pass(a, n, world, bits, p)
+            assert (s.histogram(p) == counts[rank]).all(), ("counts", n, p)
+            assert (s.starts(p) == starts[:, rank]).all(), ("starts", n, p)
+            st = s.global_shuffle(p)
+            assert list(st.sent[:world]) == sc[rank].tolist(), ("sendcounts", n, p, list(st.sent[:world]), sc[rank].tolist())
+            a = want
+            assert (s.download() == a[lo:hi]).all(), ("array after pass", n, p)
+        s.close()
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank}/{world}: multi-GPU parity ok")
