@@ -406,7 +406,8 @@ def main_cuda(args, rank, world, local_rank, own_process_group=True, tag=None):
                          "launch_frac": achieved / peak, "traffic": traffic,
                          "note": "frac is the per-pass fraction of SURVEY 8(d) over the whole step; launch_frac is the "
                                  "dominant kernel alone (32 B/element per launch / its CUDA-event duration / HBM peak); "
-                                 "traffic = ncu dram bytes of one launch (profiles/onepass_traffic.json, scaled)"},
+                                 "traffic = ncu dram bytes of one launch of that kernel (profiles/partition_traffic.json or "
+                                 "profiles/onepass_traffic.json, scaled to the launch's elements)"},
             "hist_ms_per_sort": statistics.mean(hist_ms),
             "exchange_kernel_ms_per_sort": exch_ms,
         }

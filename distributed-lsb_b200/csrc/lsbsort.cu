@@ -133,6 +133,8 @@ struct lsb_ctx {
   int64_t* localbase_v = nullptr;            // [V][65536]
   int64_t* bases_v = nullptr;                // [V][2][257]
   int dense_ready_digit = -1;                // digit whose dense counts already sit in c_all
+  unsigned* fuse_live = nullptr;             // [64] device: live-bin estimates per pass
+  bool fuse_ok[64] = {};                     // pass p's digit may be counted by pass p-1's exchange kernel
   cudaStream_t xstream = nullptr;            // exchange stream (highest priority)
   cudaEvent_t ev_sorted[LSB_MAX_PARTS] = {}, ev_x[LSB_MAX_PARTS] = {};
   std::vector<cudaEvent_t> xev;              // exchange kernel start/stop pairs (LSB_FLAG_PHASE_EVENTS)
@@ -605,17 +607,22 @@ int digit_is_constant(lsb_ctx* c, int digit, bool* constant) {
   return LSB_OK;
 }
 
-// distinct values of digit q among the first 65 536 elements of the shard, minimum over the GPUs
-int sample_live_bins(lsb_ctx* c, const PassPlan& q, int* live) {
-  unsigned* d = reinterpret_cast<unsigned*>(c->small + 36);
+// Which passes may have their digit counted by the previous pass's exchange kernel: digits of >= 12 bits that
+// take >= 2048 distinct values among the first 65 536 elements of every shard (a digit's distribution does not
+// change when the array is permuted, so the input is as good a sample as any).  One host sync, before pass 0.
+int plan_fusion(lsb_ctx* c) {
+  unsigned* d = c->fuse_live;
   const int m = (int)std::min<int64_t>(c->here, 65536);
-  live_bins_kernel<<<1, 1024, 0, c->stream>>>(c->buf[c->cur], m, q.shift, (uint32_t)((1u << q.bits) - 1), d);
-  c->launches++;
+  for (int p = 0; p < c->npasses; p++) {
+    const PassPlan q = plan_pass(c, p);
+    live_bins_kernel<<<1, 1024, 0, c->stream>>>(c->buf[c->cur], m, q.shift, (uint32_t)((1u << q.bits) - 1), d + p);
+    c->launches++;
+  }
   CU(c, cudaGetLastError());
-  if (c->G > 1) NC(c, g_nccl.AllReduce(d, d, 1, ncclUint32, ncclMin, c->comm, c->stream));
-  CU(c, cudaMemcpyAsync(c->host_skip + 8, d, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  if (c->G > 1) NC(c, g_nccl.AllReduce(d, d, (size_t)c->npasses, ncclUint32, ncclMin, c->comm, c->stream));
+  CU(c, cudaMemcpyAsync(c->host_skip, d, sizeof(unsigned) * c->npasses, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  *live = c->host_skip[8];
+  for (int p = 0; p < c->npasses; p++) c->fuse_ok[p] = plan_pass(c, p).bits >= 12 && c->host_skip[p] >= 2048;
   return LSB_OK;
 }
 
@@ -655,12 +662,8 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
   // (radix 8: 256 bins, every warp instruction replays ~32 times: 131 ms per pass measured).  Narrow digits are
   // counted by the shared-memory count kernel at the start of their own pass instead (one extra 16 B/element read).
   int next_nb = 0, next_shift = 0;
-  bool has_next = fuse_next && digit + 1 < c->npasses && plan_pass(c, digit + 1).bits >= 12;
-  if (has_next) {  // ... and wide digits that are narrow in THIS data (skewed keys), judged from a sample
-    int live = 0;
-    if ((rc = sample_live_bins(c, plan_pass(c, digit + 1), &live))) return rc;
-    has_next = live >= 2048;
-  }
+  // ... and wide digits that are narrow in THIS data (skewed keys), judged from a sample at the start of the sort
+  const bool has_next = fuse_next && digit + 1 < c->npasses && c->fuse_ok[digit + 1];
   if (has_next) {
     const PassPlan q = plan_pass(c, digit + 1);
     next_nb = 1 << q.bits;
@@ -1040,6 +1043,7 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
     CUC(cudaMalloc(&c->next_dense, sizeof(unsigned) * 65536 * V * c->G));
     CUC(cudaMalloc(&c->c_all, sizeof(unsigned) * 65536 * V * c->G));
     CUC(cudaMalloc(&c->totals, sizeof(unsigned long long) * 65536));
+    CUC(cudaMalloc(&c->fuse_live, sizeof(unsigned) * 64));
     CUC(cudaMalloc(&c->digit_base, sizeof(int64_t) * 65536));
     CUC(cudaMalloc(&c->mybase_v, sizeof(int64_t) * 65536 * V));
     int lo_prio = 0, hi_prio = 0;
@@ -1074,7 +1078,7 @@ void lsb_destroy(lsb_ctx* c) {
   if (c->host_hist) cudaFreeHost(c->host_hist);
   void* dev[] = {c->seg_start, c->seg_tiles, c->hist, c->scan_out, c->buf[0], c->buf[1], c->lookback, c->tile_counters, c->hist16, c->starts16, c->dig_meta, c->skip_flags,
                  c->counts_all, c->mybase, c->op_ctl, c->op_X, c->op_oc, c->op_F, c->op_err, c->op_prof,
-                 c->scratch[0], c->scratch[1], c->dense_local, c->dense_mine, c->next_dense, c->c_all, c->totals, c->digit_base,
+                 c->scratch[0], c->scratch[1], c->dense_local, c->dense_mine, c->next_dense, c->c_all, c->totals, c->fuse_live, c->digit_base,
                  c->mybase_v, c->localbase_v, c->bases_v, c->small, c->small_all};
   for (void* p : dev) cudaFree(p);
   for (int q = 0; q < LSB_MAX_PARTS; q++) {
@@ -1233,6 +1237,7 @@ int lsb_sort(lsb_ctx* c, lsb_stats* st) {
   if (!c->two_level) {
     if ((rc = passes_single(c, 0, c->npasses, &subpasses))) return rc;
   } else {
+    if ((rc = plan_fusion(c))) return rc;
     for (int d = 0; d < c->npasses; d++)
       if ((rc = pass_global(c, d, &subpasses, true))) return rc;
   }
