@@ -884,7 +884,7 @@ struct ExchVrArgs {
   int32_t has_next, next_shift;
   uint32_t next_mask;
   int32_t V, next_nb;
-  int64_t part;            // elements per destination part (the last part may be shorter)
+  int64_t pstart[17];      // first local index of every destination part (the same cut on every GPU); [V] = per
   unsigned* next_dense;    // [G][V][next_nb]
 };
 
@@ -895,6 +895,7 @@ template <int EX_THREADS, int EX_U>
 __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArgs a) {
   __shared__ Elt* s_dst[8];
   __shared__ long long s_lim[8];
+  __shared__ long long s_pstart[17];
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
@@ -902,6 +903,7 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArg
       s_lim[q] = (long long)q * a.per;
     }
   }
+  if (threadIdx.x < 17) s_pstart[threadIdx.x] = a.pstart[threadIdx.x];
   __syncthreads();
   unsigned pend_slot = 0xffffffffu, pend_cnt = 0;
   const int64_t chunk = (int64_t)EX_THREADS * EX_U;
@@ -928,8 +930,8 @@ __global__ void __launch_bounds__(EX_THREADS) exchange_vr_kernel(const ExchVrArg
         const long long j = g - s_lim[r];
         st_elt(s_dst[r] + j, e[u]);
         if (a.has_next) {
-          int v = (int)(j / a.part);
-          v = v < a.V ? v : a.V - 1;
+          int v = 0;
+          for (int q = 1; q < a.V; q++) v += (j >= s_pstart[q]);
           const unsigned dn = (unsigned)(e[u].key >> a.next_shift) & a.next_mask;
           const unsigned slot = (unsigned)(r * a.V + v) * (unsigned)a.next_nb + dn;
           // skew: when the whole warp counts into one slot, one lane adds the population count; a thread also

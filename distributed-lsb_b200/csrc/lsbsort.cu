@@ -30,6 +30,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -64,7 +65,10 @@ struct Tuning {
   int op_lead = 3;       // K2(s) is claimed after K1(s + lead): ~2 waves of tickets between a tile and its use
   int op_hints = 15;     // L2 eviction hints, see OnePassArgs::hints
   int op_ctas_mgpu = 3;  // one-pass CTAs per SM while an exchange kernel shares the GPU (G > 1)
-  int vparts = 8;        // parts per shard of the multi-GPU pass
+  int vparts = 16;       // parts per shard of the multi-GPU pass
+  int vramp = 130;       // part q+1 is vramp/100 times part q up to the middle of the shard, then shrinks the same
+                         // way: a pass is (sort of the first part) + (all exchanges) when the exchange is the
+                         // bottleneck and (all sorts) + (exchange of the last part) otherwise; 100 = equal parts
   int ex_ctas = 1;       // exchange CTAs per SM
   int ex_threads = 0;    // threads per exchange CTA (256 or 512; 0 = by pass shape)
   int ex_u = 4;          // 16-byte elements in flight per exchange thread (4 or 8)
@@ -121,7 +125,8 @@ struct lsb_ctx {
   // pipelined pass (virtual ranks): shard cut into V parts
   bool two_level = false;
   int V = 8;
-  int64_t vpart = 0;                         // elements per part
+  int64_t pstart[LSB_MAX_PARTS + 1] = {};    // first local index of every part (the same cut on every GPU)
+  int64_t vpart_max = 0;                     // elements of the largest part
   Elt* scratch[2] = {nullptr, nullptr};      // part-sized scratch: the sorted part until it is exchanged
   unsigned* dense_local = nullptr;           // [V][65536] counts of the full digit per part (first pass)
   unsigned* next_dense = nullptr;            // [G][V][65536] counted by the exchange kernel for the next pass
@@ -524,7 +529,7 @@ int stream_barrier(lsb_ctx* c) {
 }
 
 int64_t part_len(const lsb_ctx* c, int q) {
-  return std::max<int64_t>(0, std::min<int64_t>(c->vpart, c->here - (int64_t)q * c->vpart));
+  return std::min<int64_t>(c->pstart[q + 1], c->here) - std::min<int64_t>(c->pstart[q], c->here);
 }
 
 // virtual-rank counts of digit `digit` for every part of every GPU -> c_all[G*V][nb]
@@ -537,7 +542,7 @@ int count_parts(lsb_ctx* c, int digit) {
     const int64_t m = part_len(c, q);
     if (m <= 0) continue;
     const int off = q * nb;
-    int rc = launch_digit_hist(c, c->buf[c->cur] + (int64_t)q * c->vpart, m, &p.shift, &p.bits, &off, 1, c->dense_local, true);
+    int rc = launch_digit_hist(c, c->buf[c->cur] + c->pstart[q], m, &p.shift, &p.bits, &off, 1, c->dense_local, true);
     if (rc) return rc;
   }
   if (c->G > 1) {
@@ -677,7 +682,7 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
   for (int q = 0; q < V; q++) {
     const int64_t m = part_len(c, q);
     if (m <= 0) continue;
-    Elt* part = c->buf[c->cur] + (int64_t)q * c->vpart;
+    Elt* part = c->buf[c->cur] + c->pstart[q];
     const int64_t* segs = c->seg_start + 2 * (1 + q);
     const uint32_t* tiles = c->seg_tiles + 2 * (1 + q);
     const Elt* sorted;
@@ -722,7 +727,7 @@ int pass_global(lsb_ctx* c, int digit, int* subpasses, bool fuse_next) {
     x.next_mask = (uint32_t)(next_nb - 1);
     x.V = V;
     x.next_nb = next_nb;
-    x.part = c->vpart;
+    for (int i = 0; i <= LSB_MAX_PARTS; i++) x.pstart[i] = c->pstart[std::min(i, V)];
     x.next_dense = c->next_dense;
     // 512 threads next to partition_kernel CTAs that come and go; 256 fit beside three resident one-pass CTAs
     const int ex_threads = c->tune.ex_threads ? c->tune.ex_threads : ((c->cfg.flags & LSB_FLAG_ONE_PASS) ? 256 : 512);
@@ -883,6 +888,7 @@ int lsb_tune(const char* key, int value) {
   else if (k == "op_hints" && value >= 0 && value <= 15) g_tune.op_hints = value;
   else if (k == "op_ctas_mgpu" && value >= 0 && value <= 4) g_tune.op_ctas_mgpu = value;
   else if (k == "vparts" && value >= 1 && value <= LSB_MAX_PARTS) g_tune.vparts = value;
+  else if (k == "vramp" && value >= 100 && value <= 300) g_tune.vramp = value;
   else if (k == "ex_ctas" && value >= 1 && value <= 8) g_tune.ex_ctas = value;
   else if (k == "ex_threads" && (value == 0 || value == 256 || value == 512)) g_tune.ex_threads = value;
   else if (k == "ex_u" && (value == 4 || value == 8)) g_tune.ex_u = value;
@@ -1012,7 +1018,28 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   }
   c->two_level = c->G > 1 || (cfg->flags & LSB_FLAG_TWO_LEVEL);
   c->V = c->two_level ? c->tune.vparts : 1;
-  c->vpart = std::max<int64_t>(div_ceil(c->per, c->V), 1);
+  {
+    // cut [0, per) into V parts: equal for small shards, a geometric ramp up and down otherwise (see Tuning::vramp)
+    const int V = c->V;
+    double w[LSB_MAX_PARTS], sum = 0;
+    const bool ramp = c->per >= (int64_t)V * 4096 && c->tune.vramp > 100;
+    for (int q = 0; q < V; q++) {
+      w[q] = ramp ? std::pow(c->tune.vramp / 100.0, std::min(q, V - 1 - q)) : 1.0;
+      sum += w[q];
+    }
+    const int64_t uniform = std::max<int64_t>(div_ceil(c->per, V), 1);
+    double acc = 0;
+    c->pstart[0] = 0;
+    for (int q = 0; q < V; q++) {
+      acc += w[q];
+      int64_t e = ramp ? (int64_t)((double)c->per * (acc / sum)) / 32 * 32 : (int64_t)(q + 1) * uniform;
+      if (q == V - 1 || e > c->per) e = c->per;
+      c->pstart[q + 1] = std::max<int64_t>(e, c->pstart[q]);
+      c->vpart_max = std::max<int64_t>(c->vpart_max, c->pstart[q + 1] - c->pstart[q]);
+    }
+    for (int q = V + 1; q <= LSB_MAX_PARTS; q++) c->pstart[q] = c->per;
+    c->vpart_max = std::max<int64_t>(c->vpart_max, 1);
+  }
   {
     int64_t segs[2 * (1 + LSB_MAX_PARTS)];
     uint32_t tls[2 * (1 + LSB_MAX_PARTS)];
@@ -1036,8 +1063,8 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   }
   if (c->two_level) {
     const int V = c->V;
-    CUC(cudaMalloc(&c->scratch[0], (size_t)(c->vpart + 64) * sizeof(Elt)));
-    CUC(cudaMalloc(&c->scratch[1], (size_t)(c->vpart + 64) * sizeof(Elt)));
+    CUC(cudaMalloc(&c->scratch[0], (size_t)(c->vpart_max + 64) * sizeof(Elt)));
+    CUC(cudaMalloc(&c->scratch[1], (size_t)(c->vpart_max + 64) * sizeof(Elt)));
     CUC(cudaMalloc(&c->dense_local, sizeof(unsigned) * 65536 * V));
     CUC(cudaMalloc(&c->dense_mine, sizeof(unsigned) * 65536 * V));
     CUC(cudaMalloc(&c->next_dense, sizeof(unsigned) * 65536 * V * c->G));

@@ -89,3 +89,20 @@ def remote_fraction(sent_row, me):
 def pass_roofline_ms(m, f_remote, hbm_gbs, nvlink_gbs):
     """t_pass >= max(m*32 B / BW_hbm, m*16 B*f_remote / BW_nvlink)"""
     return max(m * 32 / (hbm_gbs * 1e9), m * 16 * f_remote / (nvlink_gbs * 1e9)) * 1e3
+
+
+def part_boundaries(per, V, ramp=1.3):
+    """first local index of each of the V parts a shard of `per` slots is cut into for the pipelined multi-GPU
+    pass (the same cut on every GPU), plus `per` at the end: equal parts for small shards, otherwise part sizes
+    grow by `ramp` up to the middle of the shard and shrink again (lsb_create in csrc/lsbsort.cu)"""
+    use_ramp = per >= V * 4096 and ramp > 1.0
+    w = [ramp ** min(q, V - 1 - q) if use_ramp else 1.0 for q in range(V)]
+    total, acc, out = sum(w), 0.0, [0]
+    uniform = max(div_ceil(per, V), 1)
+    for q in range(V):
+        acc += w[q]
+        e = int(per * (acc / total)) // 32 * 32 if use_ramp else (q + 1) * uniform
+        if q == V - 1 or e > per:
+            e = per
+        out.append(max(e, out[-1]))
+    return out

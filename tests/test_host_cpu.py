@@ -118,3 +118,16 @@ def test_virtual_ranks_do_not_change_the_pass(R, V):
         assert (counts_f.reshape(R, V, -1).sum(axis=1) == counts_c).all()
         assert (sc_f.reshape(R, V, R, V).sum(axis=(1, 3)) == sc_c).all()
         a = coarse
+
+
+def test_part_boundaries_cut_the_shard_exactly():
+    # the parts of a shard (virtual ranks) are contiguous, in order, cover [0, per) and ramp up then down
+    for per, V in ((1, 16), (100, 8), (65535, 16), (65536, 16), (1 << 21, 16), ((1 << 31) + 12345, 16), (1 << 31, 8)):
+        b = H.part_boundaries(per, V)
+        assert len(b) == V + 1 and b[0] == 0 and b[-1] == per
+        assert all(x <= y for x, y in zip(b, b[1:]))
+        sizes = [y - x for x, y in zip(b, b[1:])]
+        assert sum(sizes) == per
+        if per >= V * 4096:
+            assert sizes[0] < sizes[V // 2 - 1] and sizes[-1] < sizes[V // 2] and min(sizes) > 0
+            assert max(sizes) < 0.2 * per
