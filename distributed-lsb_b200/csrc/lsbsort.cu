@@ -1309,6 +1309,27 @@ int lsb_histogram(lsb_ctx* c, int digit, int64_t* host_counts) {
   if (rc) return rc;
   CU(c, cudaMemcpyAsync(host_counts, c->hist16, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  if (!c->two_level && !(c->cfg.flags & LSB_FLAG_ONE_PASS) && c->here > 0) {
+    // the default shape counts 8-bit sub-digits (subdigit_hist_kernel): its histograms must be the marginals of
+    // the digit's counts just returned, so a caller that checks those against the reference checks both kernels
+    SubPass subs[2];
+    int ns = 0;
+    if (p.lo_bits) subs[ns++] = {p.shift, p.lo_bits};
+    subs[ns++] = {p.shift + p.lo_bits, p.hi_bits};
+    if ((rc = launch_subdigit_hist(c, c->buf[c->cur], subs, ns))) return rc;
+    CU(c, cudaMemcpyAsync(c->host_hist, c->hist, sizeof(unsigned long long) * 256 * ns, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    std::vector<unsigned long long> lo(256, 0), hi(256, 0);
+    for (int d = 0; d < nb; d++) {
+      lo[d & ((1 << p.lo_bits) - 1)] += (unsigned long long)host_counts[d];
+      hi[d >> p.lo_bits] += (unsigned long long)host_counts[d];
+    }
+    for (int b = 0; b < 256; b++) {
+      const bool lo_ok = !p.lo_bits || c->host_hist[b] == lo[b];
+      const bool hi_ok = c->host_hist[(ns - 1) * 256 + b] == hi[b];
+      if (!lo_ok || !hi_ok) return fail(c, LSB_ERR_STATE, "lsb_histogram: sub-digit histograms are not the marginals of the digit counts");
+    }
+  }
   return LSB_OK;
 }
 
