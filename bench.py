@@ -49,13 +49,13 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+    def __init__(self, device, period_ms=100):
+        self.device, self.rows, self.proc, self.period_ms = device, [], None, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period_ms), "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -240,7 +240,7 @@ def main_cuda(args, rank, world, local_rank, own_process_group=True, tag=None):
                                  f"({v.elements} of {n} elements, hash {list(v.checksum)} vs {list(before.checksum)})")
 
     # ---- timed: exactly K steps, device time per step, max over ranks ----
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms)
     step_ms, launches, part_ms, part_launches = [], 0, 0.0, 0
     if rank == 0:
         sampler.start()
@@ -468,6 +468,7 @@ def main():
     ap.add_argument("--tune", action="append", default=[], help="key=value for lsb_tune (experiments)")
     ap.add_argument("--one-pass", action="store_true", help="measure LSB_FLAG_ONE_PASS (the one-pass kernel) as the main path")
     ap.add_argument("--no-alt", action="store_true", help="skip the short run of the other pass shape (N = 1)")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period during the timed region")
     ap.add_argument("--suite", default="", help="'name:flags;name:flags;...': several configurations in one launch, one JSON line each")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -132,11 +132,14 @@ const char* lsb_last_error(const lsb_ctx* ctx);
 const char* lsb_status_string(int status);
 
 /* Experiment knob (profiling sweeps only; the defaults are what bench.py measures): sets a
- * process-wide tunable read by the NEXT lsb_create.  Keys: "op_t1" (tiles per supertile of
- * the one-pass kernel, 1..256), "op_nx" (supertile scratch buffers), "op_lead", "op_hints"
- * (L2 eviction hints, bit mask), "op_ctas_mgpu" (one-pass CTAs per SM while an exchange kernel
- * shares the GPU), "vparts" (parts per shard, G > 1), "ex_ctas" (exchange CTAs per SM),
- * "timeout_ms" (watchdog of the one-pass kernel).  Unknown key / bad value: LSB_ERR_ARG. */
+ * process-wide tunable read by the NEXT lsb_create.  Keys: one-pass kernel -- "op_cfg" (tile
+ * shape: 0 = 512 threads x 11 elements, 1 = 256 x 11), "op_t1" (tiles per supertile, 1..256),
+ * "op_nx" (supertile scratch slots), "op_lead" (supertiles between a tile and its use),
+ * "op_hints" (L2 eviction hints, bit mask), "op_persist" (MiB of persisting L2),
+ * "op_ctas_mgpu" (one-pass CTAs per SM while an exchange kernel shares the GPU), "timeout_ms"
+ * (watchdog); multi-GPU pass -- "vparts" (parts per shard), "vramp" (size ratio of neighbouring
+ * parts x 100), "ex_ctas", "ex_threads", "ex_u" (exchange kernel shape).
+ * Unknown key / bad value: LSB_ERR_ARG. */
 int lsb_tune(const char* key, int value);
 
 /* ---- multi-GPU wiring (MPI_Init / MPI_COMM_WORLD, :588,:613-616) ----------------- */
