@@ -5,7 +5,7 @@
 // Why it is not a plain 65 536-way scatter: a tile of a few thousand elements holds about as
 // many distinct 16-bit digits as elements, so neither coalesced stores nor per-tile offsets
 // (decoupled look-back over 65 536 bins) are possible from one tile.  The pass is therefore run
-// on SUPERTILES of ~1 Mi elements that live in the 126 MB L2 between two steps:
+// on SUPERTILES of ~650 Ki elements that live in the 126 MB L2 between two steps:
 //
 //   K1(s)  tile t of supertile s: bulk-load the tile from HBM (cp.async.bulk, evict-first), rank
 //          it by the LOW byte of the digit (ballot ranking), write it back sorted by low byte to
@@ -20,10 +20,15 @@
 //          A segment larger than a tile (skewed keys) is cut into sub-tiles that run in parallel
 //          and find their offsets by decoupled look-back over the 256 high-byte bins.
 //
-// One CTA grid (2 CTAs per SM) runs both steps: work items are claimed in the fixed order
-// K1(0) K1(1) K2(0) K1(2) K2(1) ... from per-phase counters, every dependency points to an
-// item claimed earlier, so spinning on flags cannot deadlock.  HBM sees one read of the input
-// and one write of the output; the 64 B/element of supertile traffic stay in L2.
+// One persistent CTA grid (4 CTAs of 256 threads per SM) runs both steps: work items are tickets
+// from ONE counter, in the order K1(0) .. K1(lead) K2(0) K1(lead+1) K2(1) ...; every dependency
+// points to a smaller ticket and every claimed ticket is held by a running CTA, so spinning on
+// flags cannot deadlock (a watchdog turns a would-be hang into an error).  HBM sees one read of the
+// input and one write of the output as long as the scratch stays in L2 (measured: up to ~40 MB of
+// it does; DESIGN.md section 3 has the numbers and why the two-step shape is still the default).
+//
+// This file also holds digit_hist_kernel: the counts of digits of up to 16 bits (65 536 packed
+// shared-memory counters per CTA) that the pass needs up front and that the multi-GPU pass uses per part.
 #pragma once
 #include "lsb_kernels.cuh"
 
