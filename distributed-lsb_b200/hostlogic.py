@@ -106,3 +106,31 @@ def part_boundaries(per, V, ramp=1.3):
             e = per
         out.append(max(e, out[-1]))
     return out
+
+
+# ---- the one-pass kernel's work order (csrc/lsb_onepass.cuh), restated for tests ---------------------------------
+def onepass_ticket(t, nsuper, t1, lead, tiles_last=None):
+    """ticket t of the one-pass kernel -> ("K1", supertile, tile) | ("K2", supertile, segment) | None (no such item).
+    A step is t1 K1 tickets (tile of supertile `step`) followed by 256 K2 tickets (segment of supertile `step - lead`)."""
+    period = t1 + 256
+    step, r = divmod(t, period)
+    if step >= nsuper + lead:
+        return None
+    if r < t1:
+        tiles = t1 if (tiles_last is None or step != nsuper - 1) else tiles_last
+        return ("K1", step, r) if step < nsuper and r < tiles else None
+    return ("K2", step - lead, r - t1) if step >= lead else None
+
+
+def onepass_dependencies(item, nx, t1, tiles_last, nsuper):
+    """the items a work item waits for: K1(s, .) overwrites scratch slot s % nx, so every segment of supertile s - nx
+    must have gathered its pieces; K2(s, lo) needs every tile of supertile s in the scratch and the frontier of
+    segment lo advanced past supertile s - 1"""
+    kind, s, idx = item
+    if kind == "K1":
+        return [("K2", s - nx, lo) for lo in range(256)] if s >= nx else []
+    tiles = tiles_last if s == nsuper - 1 else t1
+    deps = [("K1", s, t) for t in range(tiles)]
+    if s > 0:
+        deps.append(("K2", s - 1, idx))
+    return deps

@@ -131,3 +131,22 @@ def test_part_boundaries_cut_the_shard_exactly():
         if per >= V * 4096:
             assert sizes[0] < sizes[V // 2 - 1] and sizes[-1] < sizes[V // 2] and min(sizes) > 0
             assert max(sizes) < 0.2 * per
+
+
+@pytest.mark.parametrize("nsuper,t1,lead,nx,tiles_last", [(1, 5, 1, 2, 3), (7, 3, 1, 2, 3), (9, 4, 3, 6, 1), (12, 2, 2, 3, 2), (5, 232, 3, 6, 17)])
+def test_onepass_ticket_order_has_no_forward_dependency(nsuper, t1, lead, nx, tiles_last):
+    """deadlock freedom of the one-pass kernel's spin-waits: every item is named by exactly one ticket, and every item
+    an item waits for has a SMALLER ticket (so it is held by a CTA that is already running, or done)"""
+    total = (nsuper + lead) * (t1 + 256)
+    ticket_of = {}
+    for t in range(total):
+        item = H.onepass_ticket(t, nsuper, t1, lead, tiles_last)
+        if item is not None:
+            assert item not in ticket_of
+            ticket_of[item] = t
+    assert H.onepass_ticket(total, nsuper, t1, lead, tiles_last) is None
+    k1 = sum((tiles_last if s == nsuper - 1 else t1) for s in range(nsuper))
+    assert len(ticket_of) == k1 + 256 * nsuper
+    for item, t in ticket_of.items():
+        for dep in H.onepass_dependencies(item, nx, t1, tiles_last, nsuper):
+            assert ticket_of[dep] < t, (item, dep)
