@@ -25,7 +25,8 @@
  * error instead ("errors returned by MPI calls do not need to be handled", :17-19).
  * There is NO CPU fallback: without a CUDA device lsb_create fails with LSB_ERR_CUDA.
  *
- * Threading: a context is not thread-safe.  Calls are synchronous on return.
+ * Threading: a context is not thread-safe, but contexts share no state: different contexts (also on one GPU)
+ * may be used from different threads at the same time.  Calls are synchronous on return.
  */
 #ifndef LSBSORT_H
 #define LSBSORT_H

@@ -195,6 +195,40 @@ def test_uploaded_data_and_host_path():
         assert (out == want).all() and st.elements == n
 
 
+def test_two_contexts_sort_from_two_threads():
+    # bench.py's e2e.overlapped: two contexts on one GPU, each driven by its own host thread through
+    # lsb_sort_host, must not share any state; different inputs, different pass shapes, several rounds
+    import threading
+    rng = np.random.default_rng(11)
+    n = 700001
+    ins, wants = [], []
+    for t in range(2):
+        a = np.zeros(n, dtype=lsb.ELT)
+        a["key"] = rng.integers(0, 1 << 63, n, dtype=np.uint64) >> np.uint64(7 * t)
+        a["val"] = np.arange(n, dtype=np.uint64) + np.uint64(t << 40)
+        ins.append(a)
+        wants.append(O.stable_sort(a, n))
+    sorters = [lsb.DistributedSorter(n), lsb.DistributedSorter(n, flags=L.FLAG_ONE_PASS)]
+    bad = []
+
+    def run(t):
+        out = np.empty_like(ins[t])
+        for _ in range(6):
+            out[:] = 0
+            sorters[t].sort_host(ins[t], out)
+            if not (out == wants[t]).all():
+                bad.append(t)
+
+    th = [threading.Thread(target=run, args=(t,)) for t in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for s in sorters:
+        s.close()
+    assert not bad
+
+
 def test_verifier_rejects_unsorted_and_unstable():
     n = 100000
     with lsb.DistributedSorter(n) as s:
