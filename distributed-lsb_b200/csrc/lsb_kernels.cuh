@@ -311,6 +311,7 @@ template <int THREADS_, int IPT_, int MINB_>
 struct PartCfg {
   static constexpr int THREADS = THREADS_;
   static constexpr int WARPS = THREADS_ / 32;
+  static constexpr int LOG_WARPS = THREADS_ == 1024 ? 5 : THREADS_ == 512 ? 4 : THREADS_ == 256 ? 3 : THREADS_ == 128 ? 2 : -1;
   static constexpr int IPT = IPT_;
   static constexpr int MINB = MINB_;
   static constexpr int TILE = THREADS_ * IPT_;
@@ -327,6 +328,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init_nofence(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -513,6 +517,7 @@ __device__ __forceinline__ void op_perm(const RowPlan& rp, const unsigned short*
 //   are never cleared); 5. consecutive threads write consecutive slots of a bin's run.
 // ------------------------------------------------------------------------------------
 constexpr int PT_LB_WINDOW = 4;
+constexpr int PT_MAX_CHUNKS = 16;
 constexpr uint64_t LB_VALUE_MASK = (1ULL << 56) - 1;
 
 struct PartArgs {
@@ -536,20 +541,53 @@ struct PartArgs {
   unsigned long long* run_counts;
   int32_t full_shift;
   uint32_t full_mask;
+  unsigned long long* prof;        // stage clocks, LSB_OP_PROF builds only (tools/prof_stages.py)
+  // direct mode (one segment known to the host): tile = blockIdx.x over src[d_begin, d_end); no ticket,
+  // no segment table reads -- the bulk load is issued by the CTA's first instructions
+  int32_t direct;
+  int32_t log_chunks;              // log2 of the number of bulk copies a tile arrives in (pieces of whole warps' rows)
+  int64_t d_begin, d_end;
 };
+
+// LSB_OP_PROF build (tools/ only): thread 0 of every CTA adds the clock64() delta since the previous
+// stage mark to prof[PT_PROF0 + i]; the product build compiles none of it.
+constexpr int PT_PROF0 = 24, PT_PROF_TILES = 39;
+#ifdef LSB_OP_PROF
+#define PT_T(i)                                                                        \
+  do {                                                                                 \
+    if (threadIdx.x == 0 && a.prof) {                                                  \
+      const long long now_ = clock64();                                                \
+      atomicAdd(a.prof + PT_PROF0 + (i), (unsigned long long)(now_ - pt_prof_t));      \
+      pt_prof_t = now_;                                                                \
+    }                                                                                  \
+  } while (0)
+#define PT_T_DECL long long pt_prof_t
+#define PT_T_ARG , long long pt_prof_t
+#define PT_T_PASS , pt_prof_t
+#else
+#define PT_T(i) do {} while (0)
+#define PT_T_DECL
+#define PT_T_ARG
+#define PT_T_PASS
+#endif
 
 // (round 1's kernel, kept as measured: a leaner restatement on the helpers above ran 7 % slower)
 template <class C, bool FULL, bool RUNS>
 __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
                                                unsigned* s_wtot, int tile, int seg, int count, bool first,
-                                               int first_tile) {
+                                               int first_tile PT_T_ARG) {
   Elt* s_raw = reinterpret_cast<Elt*>(smem + C::SMEM_RAW);
   unsigned short* s_perm = reinterpret_cast<unsigned short*>(smem + C::SMEM_PERM);
   unsigned short* s_whist = reinterpret_cast<unsigned short*>(smem + C::SMEM_WHIST);
   long long* s_bindst = reinterpret_cast<long long*>(smem + C::SMEM_BINDST);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  mbar_wait(s_bar, 0);
+  {  // chunked load: wait only for the piece of the tile that holds this warp's rows
+    const int lg = a.log_chunks;
+    const int chunk = warp >> (C::LOG_WARPS - lg);
+    if (chunk == 0 || chunk * (C::TILE >> lg) < count) mbar_wait(s_bar + chunk, 0);
+  }
+  PT_T(2);
 
   // ---- bins of my elements (warp-striped rows), early per-warp counts ----
   const int idx0 = warp * (32 * C::IPT) + lane;
@@ -566,12 +604,15 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
     }
   }
   __syncthreads();
+  PT_T(3);
 
   // ---- per bin: tile total (published at once), exclusive over warps, start inside the tile ----
   unsigned tile_count = 0, binstart = 0;
   uint64_t* my_state = nullptr;
+  long long my_base = 0;
   if (tid < 256) {
     my_state = a.lookback + (size_t)tile * 256 + tid;
+    my_base = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg];  // early: its latency hides under the scan
     unsigned wc[C::WARPS];
 #pragma unroll
     for (int w = 0; w < C::WARPS; w++) {
@@ -597,6 +638,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
     }
   }
   __syncthreads();
+  PT_T(4);
 
   // ---- stable ranks: slot of each element inside the tile, written as a permutation ----
   {
@@ -619,6 +661,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
     }
   }
 
+  PT_T(5);
   // ---- decoupled look-back: exclusive prefix of this bin over earlier tiles of the segment ----
   // A window of PT_LB_WINDOW predecessor words is fetched per round trip: with hundreds of tiles
   // in flight the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
@@ -628,6 +671,9 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       int look = tile - 1;
       bool done = false;
       while (!done) {
+#ifdef LSB_OP_PROF
+        if (tid == 0 && a.prof) atomicAdd(a.prof + PT_PROF0 + 10, 1ULL);
+#endif
         uint64_t v[PT_LB_WINDOW];
 #pragma unroll
         for (int i = 0; i < PT_LB_WINDOW; i++) {
@@ -648,9 +694,11 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       }
       st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
     }
-    s_bindst[tid] = a.bases[((size_t)tid << a.seg_bits) | (unsigned)seg] + (long long)excl - (long long)binstart;
+    s_bindst[tid] = my_base + (long long)excl - (long long)binstart;
   }
+  PT_T(6);
   __syncthreads();
+  PT_T(7);
 
   // ---- write: consecutive threads -> consecutive slots of a bin's run ----
 #pragma unroll
@@ -689,20 +737,61 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       }
     }
   }
+  PT_T(8);
+#ifdef LSB_OP_PROF
+  if (threadIdx.x == 0 && a.prof) atomicAdd(a.prof + PT_PROF_TILES, 1ULL);
+#endif
+}
+
+// one thread: arm the mbarriers and start the bulk copies of a tile of `cnt` elements; the tile arrives as
+// 1 << log_chunks equal pieces so that a warp starts on its rows as soon as ITS piece has landed
+template <class C>
+__device__ __forceinline__ void partition_issue_load(const PartArgs& a, unsigned char* smem, uint64_t* s_bar, long long begin, int cnt) {
+  static_assert((1 << C::LOG_WARPS) == C::WARPS && C::WARPS <= PT_MAX_CHUNKS, "a piece is a whole number of warps' rows");
+  const int lg = a.log_chunks, nch = 1 << lg, ch = C::TILE >> lg;
+  for (int q = 0; q < nch; q++) mbar_init_nofence(s_bar + q, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int q = 0; q < nch; q++) {
+    const int n = min(ch, cnt - q * ch);
+    if (n > 0) {
+      mbar_expect_tx(s_bar + q, (unsigned)n * 16u);
+      bulk_load(smem + C::SMEM_RAW + (size_t)q * ch * 16, a.src + begin + q * ch, (unsigned)n * 16u, s_bar + q);
+    }
+  }
 }
 
 template <class C, bool RUNS>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[PT_MAX_CHUNKS];
   __shared__ int s_tile, s_seg, s_count, s_first, s_first_tile;
   __shared__ unsigned s_wtot[8];
 
   const int tid = threadIdx.x;
   const int nseg = 1 << a.seg_bits;
+#ifdef LSB_OP_PROF
+  PT_T_DECL = clock64();
+#endif
 
+  if (a.direct) {
+    // tile ids in launch order (the hardware dispatches CTAs of a 1-D grid in blockIdx order, so every
+    // predecessor a look-back waits for is resident or done): the load is in flight before anything else
+    const long long begin = a.d_begin + (long long)blockIdx.x * C::TILE;
+    const long long left = a.d_end - begin;
+    const int cnt = (int)(left < C::TILE ? left : C::TILE);
+    if (tid == 0) partition_issue_load<C>(a, smem, s_bar, begin, cnt);
+    for (int i = tid; i < C::WARPS * 128; i += C::THREADS)
+      reinterpret_cast<unsigned*>(smem + C::SMEM_WHIST)[i] = 0;
+    __syncthreads();
+    PT_T(0);
+    PT_T(1);
+    if (cnt == C::TILE)
+      partition_tile<C, true, RUNS>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
+    else
+      partition_tile<C, false, RUNS>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
+    return;
+  }
   if (tid == 0) {
-    mbar_init(&s_bar, 1);
     const unsigned t = atomicAdd(a.tile_counter, 1u);
     s_tile = (t < a.seg_tile_start[nseg]) ? (int)t : -1;
     s_seg = 0;
@@ -711,6 +800,7 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
   for (int i = tid; i < C::WARPS * 128; i += C::THREADS)
     reinterpret_cast<unsigned*>(smem + C::SMEM_WHIST)[i] = 0;
   __syncthreads();
+  PT_T(0);
   const int tile = s_tile;
   if (tile < 0) return;
   // which segment owns this tile: the one with first_tile <= tile < next first_tile
@@ -730,15 +820,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
     s_count = cnt;
     s_first = (t_in == 0);
     s_first_tile = (int)a.seg_tile_start[sg];
-    mbar_expect_tx(&s_bar, (unsigned)cnt * 16u);
-    bulk_load(smem + C::SMEM_RAW, a.src + begin, (unsigned)cnt * 16u, &s_bar);
+    partition_issue_load<C>(a, smem, s_bar, begin, cnt);
   }
   __syncthreads();
+  PT_T(1);
   const int count = s_count;
   if (count == C::TILE)
-    partition_tile<C, true, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+    partition_tile<C, true, RUNS>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
   else
-    partition_tile<C, false, RUNS>(a, smem, &s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile);
+    partition_tile<C, false, RUNS>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
 }
 
 // ------------------------------------------------------------------------------------

@@ -152,7 +152,8 @@ __device__ __noinline__ bool op_wait_ge(const unsigned* p, unsigned want, const 
 #else
 #define OP_T(i) do {} while (0)
 #endif
-constexpr int OP_NPROF = 24;
+constexpr int OP_NPROF1 = 24;  // one-pass kernel's own stage clocks
+constexpr int OP_NPROF = 40;   // the whole table: 0..23 one-pass kernel, 24..39 partition_kernel (PT_PROF0)
 
 // K1 tile body after the tile has landed in shared memory: rank by the low byte, publish the
 // pieces, write the tile sorted by low byte into its place in the supertile scratch.
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
   if (tid == DISP) next_t = atomicAdd(a.ticket, 1u);
   __syncthreads();
 #ifdef LSB_OP_PROF
-  long long prof_acc[OP_NPROF];
-  for (int i = 0; i < OP_NPROF; i++) prof_acc[i] = 0;
+  long long prof_acc[OP_NPROF1];
+  for (int i = 0; i < OP_NPROF1; i++) prof_acc[i] = 0;
   long long prof_t = clock64();
 #endif
 
@@ -472,8 +473,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) onepass_kernel(const OneP
   }
 #ifdef LSB_OP_PROF
   if (tid == 0 && a.prof) {
-    for (int i = 0; i < OP_NPROF - 1; i++) atomicAdd(a.prof + i, (unsigned long long)prof_acc[i]);
-    atomicAdd(a.prof + OP_NPROF - 1, 1ULL);
+    for (int i = 0; i < OP_NPROF1 - 1; i++) atomicAdd(a.prof + i, (unsigned long long)prof_acc[i]);
+    atomicAdd(a.prof + OP_NPROF1 - 1, 1ULL);
   }
 #endif
 }

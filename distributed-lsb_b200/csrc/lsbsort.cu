@@ -73,6 +73,8 @@ struct Tuning {
   int ex_threads = 0;    // threads per exchange CTA (256 or 512; 0 = by pass shape)
   int ex_u = 4;          // 16-byte elements in flight per exchange thread (4 or 8)
   int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
+  int pt_direct = 1;     // partition_kernel: tile = blockIdx.x and the load is issued first (0 = tiles from a ticket counter)
+  int pt_chunks = 2;     // partition_kernel: log2 of the bulk copies a tile arrives in (a warp waits for its own piece)
 };
 Tuning g_tune;
 
@@ -444,6 +446,11 @@ int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits,
   a.per = INT64_MAX / 16;
   a.world = 1;
   a.dst[0] = dst;
+  a.prof = c->op_prof;
+  a.direct = g_tune.pt_direct;
+  a.log_chunks = g_tune.pt_chunks;
+  a.d_begin = 0;
+  a.d_end = m;
   c->part_elems += m;
   if (m > 0) {
     partition_kernel<TileCfg, false><<<(unsigned)div_ceil(m, c->tile), TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
@@ -893,6 +900,8 @@ int lsb_tune(const char* key, int value) {
   else if (k == "ex_threads" && (value == 0 || value == 256 || value == 512)) g_tune.ex_threads = value;
   else if (k == "ex_u" && (value == 4 || value == 8)) g_tune.ex_u = value;
   else if (k == "timeout_ms" && value >= 1) g_tune.timeout_ms = value;
+  else if (k == "pt_direct" && value >= 0 && value <= 1) g_tune.pt_direct = value;
+  else if (k == "pt_chunks" && value >= 0 && value <= 4) g_tune.pt_chunks = value;
   else return fail(nullptr, LSB_ERR_ARG, "lsb_tune: unknown key or value out of range: " + k);
   return LSB_OK;
 }

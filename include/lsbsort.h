@@ -139,7 +139,9 @@ const char* lsb_status_string(int status);
  * "op_hints" (L2 eviction hints, bit mask), "op_persist" (MiB of persisting L2),
  * "op_ctas_mgpu" (one-pass CTAs per SM while an exchange kernel shares the GPU), "timeout_ms"
  * (watchdog); multi-GPU pass -- "vparts" (parts per shard), "vramp" (size ratio of neighbouring
- * parts x 100), "ex_ctas", "ex_threads", "ex_u" (exchange kernel shape).
+ * parts x 100), "ex_ctas", "ex_threads", "ex_u" (exchange kernel shape); 8-bit scatter kernel --
+ * "pt_direct" (1 = tile index from blockIdx and the tile load issued first, 0 = tiles handed out
+ * by a ticket counter), "pt_chunks" (log2 of the bulk copies a tile arrives in, 0..4).
  * Unknown key / bad value: LSB_ERR_ARG. */
 int lsb_tune(const char* key, int value);
 

@@ -268,6 +268,24 @@ def test_many_partition_launches_recycle_tile_counters():
         assert (s.download() == want1).all()
 
 
+@pytest.mark.parametrize("direct,chunks", [(0, 0), (0, 2), (1, 0), (1, 1), (1, 3), (1, 4)])
+def test_scatter_kernel_launch_shapes(direct, chunks):
+    # the non-default ways partition_kernel gets its tiles: ticket counter instead of blockIdx, and the tile
+    # arriving in 1, 2, 8 or 16 bulk copies (full tiles, a ragged last tile, tiles smaller than one piece)
+    try:
+        lsb.tune("pt_direct", direct)
+        lsb.tune("pt_chunks", chunks)
+        for n, ranks, radix in [(5632 * 9 + 1, 2, 16), (5632 * 3 + 353, 1, 8), (300, 1, 16), (1409, 3, 11)]:
+            want = O.sort(O.generate(n, ranks), n, ranks, radix)
+            with lsb.DistributedSorter(n, ranks=ranks, radix_bits=radix) as s:
+                s.generate()
+                s.my_sort()
+                assert (s.download() == want).all(), (n, ranks, radix)
+    finally:
+        lsb.tune("pt_direct", 1)
+        lsb.tune("pt_chunks", 2)
+
+
 def test_repeated_sorts_reuse_context():
     # look-back words are tagged by generation instead of being cleared: exercise the wrap
     n = 50000

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import distributed_lsb_b200 as lsb  # noqa: E402
 from distributed_lsb_b200 import lsbsort as L  # noqa: E402
 
-DEFAULTS = {"op_cfg": 1, "op_t1": 232, "op_nx": 6, "op_lead": 3, "op_hints": 15}
+DEFAULTS = {"op_cfg": 1, "op_t1": 232, "op_nx": 6, "op_lead": 3, "op_hints": 15, "pt_direct": 1, "pt_chunks": 2}
 ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=30)
 ap.add_argument("--iters", type=int, default=3)
