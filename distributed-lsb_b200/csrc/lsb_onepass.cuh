@@ -37,21 +37,7 @@ namespace lsb {
 // ------------------------------------------------------------------------------------
 // small PTX helpers
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t l2_policy(int kind) {  // 0 normal, 1 evict_first, 2 evict_last
-  uint64_t p;
-  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void bulk_load_hint(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar,
-                                               uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(dst_smem)),
-      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
+// (l2_policy and bulk_load_hint live in lsb_kernels.cuh, next to bulk_load)
 __device__ __forceinline__ void st_elt_hint(Elt* p, const Elt& e, uint64_t policy) {
   asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;" ::"l"(p), "l"(e.key), "l"(e.val), "l"(policy)
                : "memory");

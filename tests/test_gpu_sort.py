@@ -269,21 +269,50 @@ def test_many_partition_launches_recycle_tile_counters():
 
 
 @pytest.mark.parametrize("direct,chunks", [(0, 0), (0, 2), (1, 0), (1, 1), (1, 3), (1, 4)])
-def test_scatter_kernel_launch_shapes(direct, chunks):
+def test_scatter_kernel_launch_shapes(direct, chunks, tune):
     # the non-default ways partition_kernel gets its tiles: ticket counter instead of blockIdx, and the tile
     # arriving in 1, 2, 8 or 16 bulk copies (full tiles, a ragged last tile, tiles smaller than one piece)
-    try:
-        lsb.tune("pt_direct", direct)
-        lsb.tune("pt_chunks", chunks)
-        for n, ranks, radix in [(5632 * 9 + 1, 2, 16), (5632 * 3 + 353, 1, 8), (300, 1, 16), (1409, 3, 11)]:
-            want = O.sort(O.generate(n, ranks), n, ranks, radix)
-            with lsb.DistributedSorter(n, ranks=ranks, radix_bits=radix) as s:
-                s.generate()
-                s.my_sort()
-                assert (s.download() == want).all(), (n, ranks, radix)
-    finally:
-        lsb.tune("pt_direct", 1)
-        lsb.tune("pt_chunks", 2)
+    tune("pt_direct", direct)
+    tune("pt_chunks", chunks)
+    for n, ranks, radix in [(5632 * 9 + 1, 2, 16), (5632 * 3 + 353, 1, 8), (300, 1, 16), (1409, 3, 11)]:
+        want = O.sort(O.generate(n, ranks), n, ranks, radix)
+        with lsb.DistributedSorter(n, ranks=ranks, radix_bits=radix) as s:
+            s.generate()
+            s.my_sort()
+            assert (s.download() == want).all(), (n, ranks, radix)
+
+
+_want_cache = {}
+
+
+def _want(n, ranks, radix=16, mask=ALL):
+    key = (n, ranks, radix, mask)
+    if key not in _want_cache:
+        _want_cache[key] = O.sort(O.generate(n, ranks, key_mask=mask), n, ranks, radix)
+    return _want_cache[key]
+
+
+@pytest.mark.parametrize("variant,pf_tiles,direct", [(0, 0, 1), (1, 1, 1), (1, 3, 1), (1, 0, 1), (2, 0, 1), (2, 0, 0), (3, 2, 1),
+                                                     (4, 0, 1), (5, 5, 1), (6, 0, 0), (7, 1, 1), (7, 4, 0)])
+def test_scatter_kernel_variants(variant, pf_tiles, direct, tune):
+    # the compile-time variants of partition_kernel (L2 prefetch of a later tile, look-back words loaded before the
+    # ranking phase, evict_first tile loads) and their combinations: same bytes as the oracle for one tile, a few
+    # tiles with a ragged tail (the prefetch is clipped at the end of the input), hundreds of tiles (a look-back
+    # deeper than one window), virtual ranks (several part-sized launches per pass) and ties in the keys
+    tune("pt_variant", variant)
+    tune("pt_pf_tiles", pf_tiles)
+    tune("pt_direct", direct)
+    for n, ranks, radix, flags in [(300, 1, 16, 0), (5632 * 5 + 17, 2, 16, 0), (5632 * 300 + 4001, 3, 16, 0),
+                                   (5632 * 40 + 1, 2, 11, L.FLAG_TWO_LEVEL), (5632 * 7, 1, 8, 0)]:
+        with lsb.DistributedSorter(n, ranks=ranks, radix_bits=radix, flags=flags) as s:
+            s.generate()
+            s.my_sort()
+            assert (s.download() == _want(n, ranks, radix)).all(), (n, ranks, radix, flags)
+    n = 5632 * 64 + 99
+    with lsb.DistributedSorter(n, ranks=2, key_mask=0xFFF) as s:  # 4096 distinct keys: long runs of ties, stability matters
+        s.generate()
+        s.my_sort()
+        assert (s.download() == _want(n, 2, 16, 0xFFF)).all()
 
 
 def test_repeated_sorts_reuse_context():

@@ -1,0 +1,53 @@
+#!/bin/bash
+# One call on a 1-GPU box, most important step first (the GPU-minute budget may cut the tail):
+#   1. tools/sweep_partition.py: A/B of partition_kernel's compile-time variants at n = 2^30, every sort verified;
+#      the fastest one becomes the candidate default if it beats the library as built by > 1 %
+#   2. the WHOLE `-m gpu` suite with the candidate applied through LSB_TEST_TUNE (tests/conftest.py)
+#   3. smoke + the default bench line with the candidate applied through --tune
+#   4. ncu launch list of the bench command, then one `--set full` capture of two scatter launches
+# Outputs under gpurun_out/ (copied to profiles/r2_final_* afterwards).
+cd ${GRAFT_REPO_ROOT:-.}
+mkdir -p gpurun_out
+T0=$(date +%s)
+el() { echo $(( $(date +%s) - T0 )); }
+set -x
+nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > gpurun_out/r2_final_box.txt 2>&1
+timeout 150 python tools/sweep_partition.py --log2n 30 --iters 3 --out gpurun_out/r2_final_sweep.json \
+  --set "" --set pt_variant=1 --set pt_variant=1,pt_pf_tiles=148 --set pt_variant=1,pt_pf_tiles=74 --set pt_variant=1,pt_pf_tiles=592 \
+  --set pt_variant=2 --set pt_variant=3 --set pt_variant=3,pt_pf_tiles=148 --set pt_variant=5 --set pt_variant=7 --set pt_variant=4 \
+  > gpurun_out/r2_final_sweep.log 2>&1
+cat gpurun_out/r2_final_sweep.log | cut -c1-220
+echo "elapsed $(el)"
+TUNE=$(python - <<'PY'
+import json
+try:
+    w = json.load(open("gpurun_out/r2_final_sweep.json"))["winner"] or {}
+except Exception:
+    w = {}
+print(",".join(f"{k}={v}" for k, v in w.items()))
+PY
+)
+echo "candidate: '$TUNE'" | tee gpurun_out/r2_final_candidate.txt
+LSB_TEST_TUNE="$TUNE" timeout 240 python -m pytest tests -m gpu -x -q --ignore=tests/test_multigpu.py > gpurun_out/r2_final_gpu_tests.log 2>&1
+echo "pytest rc=$? (LSB_TEST_TUNE='$TUNE')" | tee -a gpurun_out/r2_final_gpu_tests.log
+tail -4 gpurun_out/r2_final_gpu_tests.log
+echo "elapsed $(el)"
+timeout 60 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; tail -1 gpurun_out/r2_final_smoke.log
+TARGS=""
+for kv in ${TUNE//,/ }; do TARGS="$TARGS --tune $kv"; done
+timeout 200 python bench.py $TARGS > gpurun_out/r2_final_bench_1gpu.json 2> gpurun_out/r2_final_bench_1gpu.err
+echo "bench rc=$? args='$TARGS'"; tail -c 1500 gpurun_out/r2_final_bench_1gpu.json; tail -3 gpurun_out/r2_final_bench_1gpu.err
+echo "elapsed $(el)"
+if [ $(el) -lt 330 ]; then
+  timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_final_launches_bench.csv \
+    python bench.py $TARGS --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-alt > gpurun_out/r2_final_ncu_list.log 2>&1
+  echo "ncu list rc=$? elapsed $(el)"
+fi
+if [ $(el) -lt 380 ]; then
+  PT=""
+  for kv in ${TUNE//,/ }; do PT="$PT --tune $kv"; done
+  timeout 150 ncu --set full --clock-control none --import-source on -k regex:"partition_kernel" -c 2 -o gpurun_out/prof_r2_final_partition_2p30 \
+    python tools/prof_sort.py --log2n 30 --iters 1 --no-skip $PT > gpurun_out/r2_final_ncu_full.log 2>&1
+  echo "ncu full rc=$? elapsed $(el)"
+fi
+echo "done elapsed $(el)"
