@@ -38,6 +38,13 @@ for kv in ${TUNE//,/ }; do TARGS="$TARGS --tune $kv"; done
 timeout 200 python bench.py $TARGS > gpurun_out/r2_final_bench_1gpu.json 2> gpurun_out/r2_final_bench_1gpu.err
 echo "bench rc=$? args='$TARGS'"; tail -c 1500 gpurun_out/r2_final_bench_1gpu.json; tail -3 gpurun_out/r2_final_bench_1gpu.err
 echo "elapsed $(el)"
+if [ -f tools/bin/liblsbsort_prof.so ] && [ $(el) -lt 330 ]; then  # stage clocks per tile: as built, with the L2 prefetch, with the candidate
+  ( timeout 40 python tools/prof_stages.py --two-step --log2n 30
+    timeout 40 python tools/prof_stages.py --two-step --log2n 30 --tune pt_variant=1
+    timeout 40 python tools/prof_stages.py --two-step --log2n 30 --tune pt_variant=3 ) > gpurun_out/r2_final_stage_clocks.txt 2>&1
+  cat gpurun_out/r2_final_stage_clocks.txt | cut -c1-160
+  echo "elapsed $(el)"
+fi
 if [ $(el) -lt 330 ]; then
   timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_final_launches_bench.csv \
     python bench.py $TARGS --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-alt > gpurun_out/r2_final_ncu_list.log 2>&1
