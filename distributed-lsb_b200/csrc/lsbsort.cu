@@ -75,9 +75,12 @@ struct Tuning {
   int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
   int pt_direct = 1;     // partition_kernel: tile = blockIdx.x and the load is issued first (0 = tiles from a ticket counter)
   int pt_chunks = 2;     // partition_kernel: log2 of the bulk copies a tile arrives in (a warp waits for its own piece)
-  int pt_variant = 0;    // partition_kernel: bit 0 = L2 prefetch of a later tile (PT_VAR_L2PF), bit 1 = first look-back
+  int pt_variant = 1;    // partition_kernel: bit 0 = L2 prefetch of a later tile (PT_VAR_L2PF), bit 1 = first look-back
                          // window loaded before the ranking phase (PT_VAR_LBPF), bit 2 = evict_first tile loads (PT_VAR_EF)
-  int pt_pf_tiles = 0;   // PT_VAR_L2PF: how many tiles ahead (0 = the number of CTAs resident on the device)
+  int pt_pf_tiles = 0;   // PT_VAR_L2PF: how many tiles ahead; 0 = half the SM count (74 on a B200 = a quarter of the
+                         // resident CTAs, ~3 us ahead of the tile's own CTA).  Measured at 2^30 (7.09 ms per launch
+                         // without): 74 or 148 tiles -> 6.48 ms, 296 -> 6.91 ms, 592 -> 7.66 ms (the prefetched
+                         // lines do not survive in L2 next to the output stream), profiles/r2_final_sweep.log
 };
 Tuning g_tune;
 
@@ -454,7 +457,7 @@ int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits,
   a.log_chunks = g_tune.pt_chunks;
   a.d_begin = 0;
   a.d_end = m;
-  a.pf_tiles = g_tune.pt_pf_tiles > 0 ? g_tune.pt_pf_tiles : c->num_sms * TileCfg::MINB;
+  a.pf_tiles = g_tune.pt_pf_tiles > 0 ? g_tune.pt_pf_tiles : std::max(1, c->num_sms / 2);
   c->part_elems += m;
   if (m > 0) {
     const unsigned grid = (unsigned)div_ceil(m, c->tile);

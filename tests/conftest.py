@@ -22,7 +22,7 @@ def golden_dir():
 # LSB_TEST_TUNE="key=value,..." asks for: a candidate default is run through the WHOLE suite this way before it
 # becomes the built-in value (tools/run_final_1gpu.sh).  Test infrastructure only: nothing in the library reads the
 # environment.
-LIB_DEFAULT_TUNE = {"pt_direct": 1, "pt_chunks": 2, "pt_variant": 0, "pt_pf_tiles": 0}
+LIB_DEFAULT_TUNE = {"pt_direct": 1, "pt_chunks": 2, "pt_variant": 1, "pt_pf_tiles": 0}
 
 
 def session_tune():

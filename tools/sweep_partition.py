@@ -3,18 +3,19 @@
 two-step path: every configuration sorts 2^k fresh elements a few times in ONE process, verifies order,
 element count and multiset hash every time, and prints the time per sort and per scatter launch.
     python tools/sweep_partition.py --log2n 30 --set "" --set pt_variant=1 --set pt_variant=1,pt_pf_tiles=148 ...
-    --out FILE   also writes {"baseline_ms", "rows": [...], "winner": {key: value} or null}: the fastest verified
-                 configuration if it beats the first one (the baseline) by more than --margin, else null."""
+    --out FILE   also writes {"baseline_ms", "rows": [...], "winner": {key: value} or null}: the verified configuration with the lowest median
+                 time if it beats the first one (the baseline) by more than --margin, else null."""
 import argparse
 import json
 import os
+import statistics
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import distributed_lsb_b200 as lsb  # noqa: E402
 from distributed_lsb_b200 import lsbsort as L  # noqa: E402
 
-DEFAULTS = {"pt_direct": 1, "pt_chunks": 2, "pt_variant": 0, "pt_pf_tiles": 0}
+DEFAULTS = {"pt_direct": 1, "pt_chunks": 2, "pt_variant": 1, "pt_pf_tiles": 0}  # the library's built-in values
 ap = argparse.ArgumentParser()
 ap.add_argument("--log2n", type=int, default=30)
 ap.add_argument("--iters", type=int, default=3)
@@ -44,9 +45,11 @@ for idx, cfg in enumerate(a.set or [""]):
                 assert list(v.checksum) == before and v.elements == n and not v.order_violations
                 ms.append(st.device_ms)
                 launch.append(st.partition_ms / max(st.partition_launches, 1))
-        row.update(ok=True, sort_ms=min(ms), all_ms=[round(x, 3) for x in ms], launch_ms=min(launch))
-        print(f"[{cfg or 'as built'}] n=2^{a.log2n}: sort ms {row['all_ms']} best {min(ms):.3f} = {n / min(ms) / 1e3:.0f} M/s; "
-              f"scatter launch {min(launch):.3f} ms = {n * 32 / min(launch) / 1e6:.0f} GB/s; verified", flush=True)
+        # the median, not the best: a faster kernel runs into the power cap after the first sort or two
+        med, lmed = statistics.median(ms), statistics.median(launch)
+        row.update(ok=True, sort_ms=med, best_ms=min(ms), all_ms=[round(x, 3) for x in ms], launch_ms=lmed)
+        print(f"[{cfg or 'as built'}] n=2^{a.log2n}: sort ms {row['all_ms']} median {med:.3f} = {n / med / 1e3:.0f} M/s; "
+              f"scatter launch {lmed:.3f} ms = {n * 32 / lmed / 1e6:.0f} GB/s; verified", flush=True)
     except (lsb.LsbError, AssertionError) as e:
         row["error"] = repr(e)
         print(f"[{cfg}] FAILED: {e!r}", flush=True)
