@@ -557,30 +557,21 @@ struct PartArgs {
   int64_t per;                     // destination shard size (global index / per = shard)
   int32_t world;
   Elt* dst[8];                     // destination shard base pointers (peer-mapped for g != my)
-  // RUNS kernels only: the input is already grouped by the low bits of a wider digit, so the
-  // sorted tile is ordered by that full digit; count its runs into run_counts[digit]
-  unsigned long long* run_counts;
-  int32_t full_shift;
-  uint32_t full_mask;
   unsigned long long* prof;        // stage clocks, LSB_OP_PROF builds only (tools/prof_stages.py)
   // direct mode (one segment known to the host): tile = blockIdx.x over src[d_begin, d_end); no ticket,
   // no segment table reads -- the bulk load is issued by the CTA's first instructions
   int32_t direct;
   int32_t log_chunks;              // log2 of the number of bulk copies a tile arrives in (pieces of whole warps' rows)
   int64_t d_begin, d_end;
-  int32_t pf_tiles;                // PT_VAR_L2PF: tile blockIdx.x + pf_tiles is pulled into L2 when this tile starts
+  int32_t pf_tiles;                // L2PF: tile blockIdx.x + pf_tiles is pulled into L2 when this tile starts
 };
 
-// compile-time variants of partition_kernel (bit mask; lsb_tune "pt_variant"):
-//   PT_VAR_L2PF  direct mode: the CTA of tile t also starts a bulk L2 prefetch of tile t + pf_tiles, so the tile
-//                load of the CTA that gets that tile one CTA lifetime later is an L2 hit (the HBM queueing moves
-//                off the CTA's critical path; DRAM traffic is unchanged as long as the line survives ~10 us in L2)
-//   PT_VAR_LBPF  the first window of look-back words is loaded BEFORE the ranking phase and consumed after it
-//                (a word only ever goes not-ready -> aggregate -> inclusive within a launch, so an older value is
-//                still a correct one); saves one dependent L2 round trip of the walk
-//   PT_VAR_EF    the tile load carries an L2 evict_first policy: a tile is read exactly once, its lines are dead
-//                in L2 as soon as they have been copied to shared memory
-constexpr int PT_VAR_L2PF = 1, PT_VAR_LBPF = 2, PT_VAR_EF = 4, PT_NUM_VARIANTS = 8;
+// L2PF (compile-time; lsb_tune "pt_variant" 1 = default, 0 = off): in direct mode the CTA of tile t also starts a bulk
+// L2 prefetch of tile t + pf_tiles, so the tile load of the CTA that gets that tile a few microseconds later is an L2 hit:
+// the HBM queueing moves off the CTA's serial path (7.09 -> 6.48 ms per launch at 2^30) and DRAM traffic is unchanged as
+// long as the lines survive in L2 until then (distance 74..148 tiles; at 296 half the gain is gone, at 592 it is a loss).
+// Two more variants were A/B-measured at commit a1530c7 and removed: the first look-back window loaded before the ranking
+// phase (+3 % time) and evict_first tile loads (no gain), profiles/r2_final_sweep.log.
 
 // LSB_OP_PROF build (tools/ only): thread 0 of every CTA adds the clock64() delta since the previous
 // stage mark to prof[PT_PROF0 + i]; the product build compiles none of it.
@@ -605,7 +596,7 @@ constexpr int PT_PROF0 = 24, PT_PROF_TILES = 39;
 #endif
 
 // (round 1's kernel, kept as measured: a leaner restatement on the helpers above ran 7 % slower)
-template <class C, bool FULL, bool RUNS, int VAR>
+template <class C, bool FULL>
 __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char* smem, uint64_t* s_bar,
                                                unsigned* s_wtot, int tile, int seg, int count, bool first,
                                                int first_tile PT_T_ARG) {
@@ -673,18 +664,6 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
   __syncthreads();
   PT_T(4);
 
-  // PT_VAR_LBPF: the nearest PT_LB_WINDOW predecessor words, in flight while the ranks are computed
-  uint64_t lb_pre[PT_LB_WINDOW];
-  if constexpr ((VAR & PT_VAR_LBPF) != 0) {
-    if (tid < 256 && !first) {
-#pragma unroll
-      for (int i = 0; i < PT_LB_WINDOW; i++) {
-        const int t = tile - 1 - i;
-        lb_pre[i] = (t >= first_tile) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
-      }
-    }
-  }
-
   // ---- stable ranks: slot of each element inside the tile, written as a permutation ----
   {
     unsigned short* wh = s_whist + warp * 256;
@@ -712,35 +691,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
   // in flight the walk is ~10 tiles deep, and one dependent L2 access per tile would dominate.
   if (tid < 256) {
     uint64_t excl = 0;
-    if constexpr ((VAR & PT_VAR_LBPF) != 0) {
-      if (!first) {
-        int look = tile - 1;
-        uint64_t v[PT_LB_WINDOW];
-#pragma unroll
-        for (int i = 0; i < PT_LB_WINDOW; i++) v[i] = lb_pre[i];
-        for (;;) {
-          bool done = false;
-          int used = 0;
-#pragma unroll
-          for (int i = 0; i < PT_LB_WINDOW; i++) {
-            if (!done && used == i) {
-              const uint64_t tag = v[i] & ~LB_VALUE_MASK;
-              if (tag == a.tag_inc) { excl += v[i] & LB_VALUE_MASK; done = true; }
-              else if (tag == a.tag_agg) { excl += v[i] & LB_VALUE_MASK; used = i + 1; }
-            }
-          }
-          if (done) break;
-          look -= used;
-          if (used == 0) __nanosleep(20);
-#pragma unroll
-          for (int i = 0; i < PT_LB_WINDOW; i++) {
-            const int t = look - i;
-            v[i] = (t >= first_tile) ? ld_relaxed_gpu(a.lookback + (size_t)t * 256 + tid) : 0;
-          }
-        }
-        st_relaxed_gpu(my_state, a.tag_inc | (excl + tile_count));
-      }
-    } else if (!first) {
+    if (!first) {
       int look = tile - 1;
       bool done = false;
       while (!done) {
@@ -795,20 +746,6 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
       }
       st_elt(out, el);
     }
-    if (RUNS) {
-      // localShuffle's counts of the FULL digit (:226-229) as a by-product: the sorted tile is
-      // non-decreasing in the full digit, so each warp adds the length of every run it sees
-      const unsigned d = valid ? ((unsigned)(el.key >> a.full_shift) & a.full_mask) : 0xffffffffu;
-      const unsigned prev = __shfl_up_sync(0xffffffffu, d, 1);
-      const bool head = valid && (lane == 0 || d != prev);
-      const unsigned heads = __ballot_sync(0xffffffffu, head);
-      const unsigned nvalid = FULL ? 32u : (unsigned)__popc(__ballot_sync(0xffffffffu, valid));
-      if (head) {
-        const unsigned after = heads & ~((2u << lane) - 1u);
-        const unsigned end = after ? (unsigned)(__ffs(after) - 1) : nvalid;
-        atomicAdd(a.run_counts + d, (unsigned long long)(end - (unsigned)lane));
-      }
-    }
   }
   PT_T(8);
 #ifdef LSB_OP_PROF
@@ -818,7 +755,7 @@ __device__ __forceinline__ void partition_tile(const PartArgs& a, unsigned char*
 
 // one thread: arm the mbarriers and start the bulk copies of a tile of `cnt` elements; the tile arrives as
 // 1 << log_chunks equal pieces so that a warp starts on its rows as soon as ITS piece has landed
-template <class C, int VAR>
+template <class C>
 __device__ __forceinline__ void partition_issue_load(const PartArgs& a, unsigned char* smem, uint64_t* s_bar, long long begin, int cnt) {
   static_assert((1 << C::LOG_WARPS) == C::WARPS && C::WARPS <= PT_MAX_CHUNKS, "a piece is a whole number of warps' rows");
   const int lg = a.log_chunks, nch = 1 << lg, ch = C::TILE >> lg;
@@ -828,15 +765,12 @@ __device__ __forceinline__ void partition_issue_load(const PartArgs& a, unsigned
     const int n = min(ch, cnt - q * ch);
     if (n > 0) {
       mbar_expect_tx(s_bar + q, (unsigned)n * 16u);
-      if constexpr ((VAR & PT_VAR_EF) != 0)
-        bulk_load_hint(smem + C::SMEM_RAW + (size_t)q * ch * 16, a.src + begin + q * ch, (unsigned)n * 16u, s_bar + q, l2_policy(1));
-      else
-        bulk_load(smem + C::SMEM_RAW + (size_t)q * ch * 16, a.src + begin + q * ch, (unsigned)n * 16u, s_bar + q);
+      bulk_load(smem + C::SMEM_RAW + (size_t)q * ch * 16, a.src + begin + q * ch, (unsigned)n * 16u, s_bar + q);
     }
   }
 }
 
-template <class C, bool RUNS, int VAR = 0>
+template <class C, bool L2PF>
 __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const PartArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t s_bar[PT_MAX_CHUNKS];
@@ -855,8 +789,8 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
     const long long begin = a.d_begin + (long long)blockIdx.x * C::TILE;
     const long long left = a.d_end - begin;
     const int cnt = (int)(left < C::TILE ? left : C::TILE);
-    if (tid == 0) partition_issue_load<C, VAR>(a, smem, s_bar, begin, cnt);
-    if constexpr ((VAR & PT_VAR_L2PF) != 0) {
+    if (tid == 0) partition_issue_load<C>(a, smem, s_bar, begin, cnt);
+    if constexpr (L2PF) {
       if (tid == 0) {
         const long long pb = begin + (long long)a.pf_tiles * C::TILE;
         const long long pl = a.d_end - pb;
@@ -869,9 +803,9 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
     PT_T(0);
     PT_T(1);
     if (cnt == C::TILE)
-      partition_tile<C, true, RUNS, VAR>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
+      partition_tile<C, true>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
     else
-      partition_tile<C, false, RUNS, VAR>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
+      partition_tile<C, false>(a, smem, s_bar, s_wtot, (int)blockIdx.x, 0, cnt, blockIdx.x == 0, 0 PT_T_PASS);
     return;
   }
   if (tid == 0) {
@@ -903,15 +837,15 @@ __global__ void __launch_bounds__(C::THREADS, C::MINB) partition_kernel(const Pa
     s_count = cnt;
     s_first = (t_in == 0);
     s_first_tile = (int)a.seg_tile_start[sg];
-    partition_issue_load<C, VAR>(a, smem, s_bar, begin, cnt);
+    partition_issue_load<C>(a, smem, s_bar, begin, cnt);
   }
   __syncthreads();
   PT_T(1);
   const int count = s_count;
   if (count == C::TILE)
-    partition_tile<C, true, RUNS, VAR>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
+    partition_tile<C, true>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
   else
-    partition_tile<C, false, RUNS, VAR>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
+    partition_tile<C, false>(a, smem, s_bar, s_wtot, tile, s_seg, count, s_first, s_first_tile PT_T_PASS);
 }
 
 // ------------------------------------------------------------------------------------

@@ -75,9 +75,8 @@ struct Tuning {
   int timeout_ms = 4000; // watchdog of the one-pass kernel's waits
   int pt_direct = 1;     // partition_kernel: tile = blockIdx.x and the load is issued first (0 = tiles from a ticket counter)
   int pt_chunks = 2;     // partition_kernel: log2 of the bulk copies a tile arrives in (a warp waits for its own piece)
-  int pt_variant = 1;    // partition_kernel: bit 0 = L2 prefetch of a later tile (PT_VAR_L2PF), bit 1 = first look-back
-                         // window loaded before the ranking phase (PT_VAR_LBPF), bit 2 = evict_first tile loads (PT_VAR_EF)
-  int pt_pf_tiles = 0;   // PT_VAR_L2PF: how many tiles ahead; 0 = half the SM count (74 on a B200 = a quarter of the
+  int pt_variant = 1;    // partition_kernel: 1 = L2 prefetch of a later tile (template L2PF), 0 = off
+  int pt_pf_tiles = 0;   // L2PF: how many tiles ahead; 0 = half the SM count (74 on a B200 = a quarter of the
                          // resident CTAs, ~3 us ahead of the tile's own CTA).  Measured at 2^30 (7.09 ms per launch
                          // without): 74 or 148 tiles -> 6.48 ms, 296 -> 6.91 ms, 592 -> 7.66 ms (the prefetched
                          // lines do not survive in L2 next to the output stream), profiles/r2_final_sweep.log
@@ -461,16 +460,10 @@ int launch_partition(lsb_ctx* c, const Elt* src, int64_t m, int shift, int bits,
   c->part_elems += m;
   if (m > 0) {
     const unsigned grid = (unsigned)div_ceil(m, c->tile);
-    switch (a.direct ? g_tune.pt_variant : (g_tune.pt_variant & ~PT_VAR_L2PF)) {  // the prefetch needs blockIdx-ordered tiles
-      case 1: partition_kernel<TileCfg, false, 1><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 2: partition_kernel<TileCfg, false, 2><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 3: partition_kernel<TileCfg, false, 3><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 4: partition_kernel<TileCfg, false, 4><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 5: partition_kernel<TileCfg, false, 5><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 6: partition_kernel<TileCfg, false, 6><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      case 7: partition_kernel<TileCfg, false, 7><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-      default: partition_kernel<TileCfg, false, 0><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a); break;
-    }
+    if (a.direct && g_tune.pt_variant)  // the prefetch needs blockIdx-ordered tiles
+      partition_kernel<TileCfg, true><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
+    else
+      partition_kernel<TileCfg, false><<<grid, TileCfg::THREADS, TileCfg::SMEM, c->stream>>>(a);
     c->launches++;
   }
   CU(c, cudaGetLastError());
@@ -919,7 +912,7 @@ int lsb_tune(const char* key, int value) {
   else if (k == "timeout_ms" && value >= 1) g_tune.timeout_ms = value;
   else if (k == "pt_direct" && value >= 0 && value <= 1) g_tune.pt_direct = value;
   else if (k == "pt_chunks" && value >= 0 && value <= 4) g_tune.pt_chunks = value;
-  else if (k == "pt_variant" && value >= 0 && value < PT_NUM_VARIANTS) g_tune.pt_variant = value;
+  else if (k == "pt_variant" && value >= 0 && value <= 1) g_tune.pt_variant = value;
   else if (k == "pt_pf_tiles" && value >= 0 && value <= 65536) g_tune.pt_pf_tiles = value;
   else return fail(nullptr, LSB_ERR_ARG, "lsb_tune: unknown key or value out of range: " + k);
   return LSB_OK;
@@ -1001,19 +994,12 @@ int lsb_create(lsb_ctx** out, const lsb_config* cfg) {
   CUC(cudaMalloc(&c->counts_all, sizeof(unsigned long long) * 65536 * c->G));
   CUC(cudaMalloc(&c->mybase, sizeof(int64_t) * 65536));
   // one-pass kernel: supertile scratch, piece table, control block, frontier table
-#define LSB_PT_ATTR(V)                                                                                                        \
-  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM)); \
-  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, false, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  LSB_PT_ATTR(0)
-  LSB_PT_ATTR(1)
-  LSB_PT_ATTR(2)
-  LSB_PT_ATTR(3)
-  LSB_PT_ATTR(4)
-  LSB_PT_ATTR(5)
-  LSB_PT_ATTR(6)
-  LSB_PT_ATTR(7)
+#define LSB_PT_ATTR(V)                                                                                                     \
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg::SMEM));     \
+  CUC(cudaFuncSetAttribute(partition_kernel<TileCfg, V>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  LSB_PT_ATTR(false)
+  LSB_PT_ATTR(true)
 #undef LSB_PT_ATTR
-  static_assert(PT_NUM_VARIANTS == 8, "one launch case and one attribute line per variant");
 #define LSB_OP_ATTR(CFG, B)                                                                                       \
   CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, CFG::SMEM));     \
   CUC(cudaFuncSetAttribute(onepass_kernel<CFG, B>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));

@@ -141,9 +141,8 @@ const char* lsb_status_string(int status);
  * (watchdog); multi-GPU pass -- "vparts" (parts per shard), "vramp" (size ratio of neighbouring
  * parts x 100), "ex_ctas", "ex_threads", "ex_u" (exchange kernel shape); 8-bit scatter kernel --
  * "pt_direct" (1 = tile index from blockIdx and the tile load issued first, 0 = tiles handed out
- * by a ticket counter), "pt_chunks" (log2 of the bulk copies a tile arrives in, 0..4), "pt_variant" (bit mask of
- * compile-time variants: 1 = the CTA of tile t also bulk-prefetches tile t + pt_pf_tiles into L2 [default],
- * 2 = first look-back window loaded before the ranking phase, 4 = evict_first tile loads), "pt_pf_tiles"
+ * by a ticket counter), "pt_chunks" (log2 of the bulk copies a tile arrives in, 0..4), "pt_variant" (1 = the CTA of tile t
+ * also bulk-prefetches tile t + pt_pf_tiles into L2 [default], 0 = no prefetch), "pt_pf_tiles"
  * (prefetch distance in tiles, 0 = half the SM count).
  * Unknown key / bad value: LSB_ERR_ARG. */
 int lsb_tune(const char* key, int value);

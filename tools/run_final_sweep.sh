@@ -13,7 +13,8 @@ el() { echo $(( $(date +%s) - T0 )); }
 set -x
 nvidia-smi --query-gpu=name,clocks.max.sm,memory.total --format=csv,noheader > gpurun_out/${TAG:-r2_final}_box.txt 2>&1
 # first call of the round: SETS unset (all variants, coarse prefetch distances); second call: the fine sweep below
-COARSE='--set "" --set pt_variant=1 --set pt_variant=1,pt_pf_tiles=148 --set pt_variant=1,pt_pf_tiles=74 --set pt_variant=1,pt_pf_tiles=592 --set pt_variant=2 --set pt_variant=3 --set pt_variant=3,pt_pf_tiles=148 --set pt_variant=5 --set pt_variant=7 --set pt_variant=4'
+# (the first call of the round also had pt_variant 2..7: look-back preload and evict_first loads, removed since)
+COARSE='--set "" --set pt_variant=0 --set pt_variant=1,pt_pf_tiles=37 --set pt_variant=1,pt_pf_tiles=148 --set pt_variant=1,pt_pf_tiles=296 --set pt_variant=1,pt_pf_tiles=592'
 SETS=${SETS:-$COARSE}
 eval timeout 150 python tools/sweep_partition.py --log2n 30 --iters ${ITERS:-3} --out gpurun_out/${TAG:-r2_final}_sweep.json $SETS \
   > gpurun_out/${TAG:-r2_final}_sweep.log 2>&1
@@ -50,8 +51,7 @@ if [ -n "$EXTRA" ]; then  # the other 1-GPU points with the candidate: 2^31, rad
 fi
 if [ -f tools/bin/liblsbsort_prof.so ] && [ $(el) -lt 330 ]; then  # stage clocks per tile: as built, with the L2 prefetch, with the candidate
   ( timeout 40 python tools/prof_stages.py --two-step --log2n 30
-    timeout 40 python tools/prof_stages.py --two-step --log2n 30 --tune pt_variant=1
-    timeout 40 python tools/prof_stages.py --two-step --log2n 30 --tune pt_variant=3 ) > gpurun_out/${TAG:-r2_final}_stage_clocks.txt 2>&1
+    timeout 40 python tools/prof_stages.py --two-step --log2n 30 --tune pt_variant=0 ) > gpurun_out/${TAG:-r2_final}_stage_clocks.txt 2>&1
   cat gpurun_out/${TAG:-r2_final}_stage_clocks.txt | cut -c1-160
   echo "elapsed $(el)"
 fi
