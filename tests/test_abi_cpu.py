@@ -55,3 +55,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower().replace("# oracle", ""), f
+
+
+def test_tune_keys_match_the_header_and_conftest():
+    """every lsb_tune key the header documents is accepted, out-of-range values and unknown keys are LSB_ERR_ARG, and
+    the partition_kernel defaults tests/conftest.py restores are values the library accepts"""
+    import re
+    if not os.path.exists(lsb.library_path()):
+        pytest.skip("liblsbsort.so not built")
+    from conftest import LIB_DEFAULT_TUNE, apply_session_tune
+    header = open(os.path.join(ROOT, "include", "lsbsort.h")).read()
+    doc = header[header.index("process-wide tunable"):header.index("int lsb_tune(")]
+    keys = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert {"op_t1", "vparts", "ex_u", "pt_direct", "pt_chunks", "pt_variant", "pt_pf_tiles"} <= keys
+    sane = {"op_cfg": 1, "op_t1": 232, "op_nx": 6, "op_lead": 3, "op_hints": 15, "op_persist": 0, "op_ctas_mgpu": 3,
+            "timeout_ms": 4000, "vparts": 16, "vramp": 130, "ex_ctas": 1, "ex_threads": 0, "ex_u": 4}
+    sane.update(LIB_DEFAULT_TUNE)
+    assert keys == set(sane), keys ^ set(sane)
+    try:
+        for k, v in sane.items():
+            lsb.tune(k, v)  # the library's own defaults: accepted, and nothing changes for later tests
+        for k, bad in [("pt_variant", 2), ("pt_variant", -1), ("pt_chunks", 5), ("pt_direct", 2), ("pt_pf_tiles", -1),
+                       ("pt_pf_tiles", 1 << 20), ("vparts", 0), ("ex_u", 5), ("no_such_key", 1)]:
+            with pytest.raises(lsb.LsbError):
+                lsb.tune(k, bad)
+    finally:
+        apply_session_tune()
